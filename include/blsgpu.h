@@ -1,0 +1,129 @@
+/*
+ * blsgpu.h — C ABI of libblsgpu.so: B200 (sm_100a) batch BLS12-381 signature verification.
+ *
+ * This is the drop-in boundary for nim-blscurve's batch-verification path: the Nim module
+ * blscurve/cuda/blsgpu_abi.nim binds exactly these symbols and the bodies of
+ * batchVerifySerial / batchVerifyParallel / batchVerify / aggregateAll / combine call them instead
+ * of BLST.  File:line references are into /root/reference.
+ *
+ * Data formats are the reference's in-memory formats, byte for byte:
+ *   SignatureSet = (PublicKey, array[32,byte], Signature)      blscurve/bls_batch_verifier.nim:34
+ *     = blst_p1_affine (2 x 48 B) | 32 B message | blst_p2_affine (4 x 48 B) = 320 bytes, no padding;
+ *     every Fp is 6 x u64 little-endian limbs in Montgomery form    vendor/blst/bindings/blst.h:63,:170,:197
+ *   affine infinity = all-zero bytes.
+ *   GT output = 576 bytes as blst_bendian_from_fp12 writes them     vendor/blst/src/fp12_tower.c:773-786
+ *
+ * Return convention for verification calls: 1 = valid, 0 = invalid (same booleans as the reference,
+ * including false on empty input — bls_batch_verifier.nim:137, :312 — and on an infinite public key —
+ * vendor/blst/src/aggregate.c:296), negative = runtime failure (CUDA error, bad argument); the text is
+ * available from blsgpu_last_error().  There is no CPU fallback: without a CUDA device every call fails.
+ *
+ * Threading: one in-flight call per blsgpu_ctx (like one BatchedBLSVerifierCache per caller,
+ * bls_batch_verifier.nim:389-391); different contexts may be used from different host threads.
+ * Host pointers are borrowed for the duration of the call only.
+ */
+#ifndef BLSGPU_H
+#define BLSGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct blsgpu_ctx blsgpu_ctx;
+
+#define BLSGPU_SET_BYTES 320
+#define BLSGPU_GT_BYTES 576
+#define BLSGPU_ERR_CUDA (-1)
+#define BLSGPU_ERR_ARG (-2)
+#define BLSGPU_ERR_CAPACITY (-3)
+
+/* Number of CUDA devices visible (0 when none: the library cannot work). */
+int blsgpu_device_count(void);
+
+/* Replaces BatchedBLSVerifierCache.init (bls_batch_verifier.nim:108-119): device scratch for batches of up
+ * to max_sets signature sets on CUDA device `device`.  NULL on failure (see blsgpu_last_error(NULL)). */
+blsgpu_ctx *blsgpu_create(int device, size_t max_sets);
+void blsgpu_destroy(blsgpu_ctx *ctx);
+const char *blsgpu_last_error(const blsgpu_ctx *ctx);
+size_t blsgpu_capacity(const blsgpu_ctx *ctx);
+
+/* Run on an existing CUDA stream (cudaStream_t passed as void*; NULL = the context's own stream). */
+int blsgpu_set_stream(blsgpu_ctx *ctx, void *cuda_stream);
+
+/* Random-linear-combination scalars exactly as the reference derives them
+ * (blst_min_pubkey_sig_core.nim:476-505, :545-556; chunking parallel_chunks.nim:42-55):
+ *   chunks == 0: serial derivation (batchVerifySerial): seed = SHA256(srb)
+ *   chunks  > 0: batchVerifyParallel with numThreads = chunks: numBatches = min(n, chunks),
+ *                seed_c = SHA256(srb || LE64(c)); per set seed <- SHA256(seed) until LE64(seed[0..8]) != 0.
+ * Computed on the device; out receives n little-endian 64-bit scalars. */
+int blsgpu_rlc_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, uint32_t chunks, uint64_t *out);
+
+/* Replaces the body of batchVerifySerial (:121-160) / batchVerifyParallel (:296-371):
+ * ctx.init + update* + commit + merge + finalVerify on BLST become one device pipeline.
+ *   sets     n x 320 bytes, host memory
+ *   chunks   scalar derivation mode as above (ignored when scalars != NULL)
+ *   scalars  optional n explicit 64-bit blinding scalars (all must be non-zero)
+ *   gt_out   optional 576 bytes: the GT value after final exponentiation, FE(conj(ML(S,G1)) * prod ML(...))
+ */
+int blsgpu_batch_verify(blsgpu_ctx *ctx, const void *sets, size_t n, const uint8_t srb[32], uint32_t chunks,
+                        const uint64_t *scalars, uint8_t gt_out[576]);
+
+/* Same with the sets already resident in device memory (d_sets: device pointer, n x 320 bytes). */
+int blsgpu_batch_verify_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n, const uint8_t srb[32],
+                            uint32_t chunks, const uint64_t *scalars, uint8_t gt_out[576]);
+
+/* Multi-GPU: one rank's share of a batch of total_n sets.  The rank owns the global index range
+ * [first, first + n) (the balanced split of parallel_chunks.nim over ranks) and derives the scalars of
+ * exactly those indices from the global (total_n, chunks) derivation, so the result does not depend on
+ * the number of ranks.  Output: the 576-byte Fp12 partial  conj(ML(S_k, G1)) * prod_{i in k} ML([r_i]pk_i, H(m_i))
+ * in the reference's in-memory Fp12 layout (what blst_pairing_merge multiplies, aggregate.c:410-458), and
+ * *flags != 0 if a set of this share must fail the batch (infinite public key).
+ * sets_on_device != 0: `sets` is a device pointer. */
+int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_device, size_t n, size_t first, size_t total_n,
+                   const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, uint8_t partial_out[576],
+                   int *flags);
+
+/* Product of `count` gathered partials, ONE final exponentiation, comparison with 1 (aggregate.c:494-500). */
+int blsgpu_finalize(blsgpu_ctx *ctx, const uint8_t *partials, size_t count, uint8_t gt_out[576]);
+
+/* hash_to_G2 for n messages of msg_len bytes each (replaces blst_hash_to_g2 + blst_p2_to_affine,
+ * vendor/blst/src/map_to_g2.c:388-396): out_compressed (nullable) n x 96 bytes Zcash compressed form,
+ * out_affine (nullable) n x 192 bytes blst_p2_affine.  dst_len <= 255. */
+int blsgpu_hash_to_g2(blsgpu_ctx *ctx, const uint8_t *msgs, size_t n, size_t msg_len, const uint8_t *dst,
+                      size_t dst_len, uint8_t *out_compressed, uint8_t *out_affine);
+
+/* aggregateAll (blst_min_pubkey_sig_core.nim:179-195): sum of n affine points; 0 on empty input. */
+int blsgpu_aggregate_g1(blsgpu_ctx *ctx, const void *points96, size_t n, uint8_t out96[96]);
+int blsgpu_aggregate_g2(blsgpu_ctx *ctx, const void *points192, size_t n, uint8_t out192[192]);
+
+/* G1 multi-scalar multiplication (replaces blst_p1s_mult_pippenger + blst_p1_to_affine,
+ * vendor/blst/src/multi_scalar.c:415-434; call shape of benchmarks/bls12381_msm_g1.nim:57-59):
+ * points n x 96 bytes affine, scalars n x ceil(nbits/8) bytes little-endian, out = affine sum. */
+int blsgpu_msm_g1(blsgpu_ctx *ctx, const void *points96, const void *scalars, size_t n, size_t nbits,
+                  uint8_t out96[96]);
+int blsgpu_msm_g1_dev(blsgpu_ctx *ctx, const void *d_points96, const void *d_scalars, size_t n, size_t nbits,
+                      uint8_t out96[96]);
+
+/* Per-stage device times (ms) of the last batch_verify/partial call on this context, measured with CUDA
+ * events on the call's stream.  Returns the number of stages written (<= max); names via blsgpu_stage_name. */
+int blsgpu_last_stage_ms(const blsgpu_ctx *ctx, float *ms, int max);
+const char *blsgpu_stage_name(int stage);
+/* Kernel launches issued by the last call. */
+int blsgpu_last_launches(const blsgpu_ctx *ctx);
+
+/* Test/diagnostic entry points */
+/* Fp unit ops on the device: op 0=mul 1=add 2=sub 3=sqr 4=inverse; a,b,out: n x 48 bytes (Montgomery). */
+int blsgpu_test_fp(blsgpu_ctx *ctx, int op, const void *a, const void *b, size_t n, void *out);
+/* Integer-multiply pipe microbenchmark: returns measured 32x32->64 multiply-accumulates per second. */
+double blsgpu_imad_peak(blsgpu_ctx *ctx, int wide);
+/* Generate n valid signature sets on the device (synthetic workload for benchmarks):
+ * sk_i = 1 + (SHA256(seed || LE64(first+i)) mod 2^250), pk = [sk]G1, msg = SHA256("blsgpu" || LE64(first+i)),
+ * sig = [sk]H(msg).  out: device pointer if out_on_device, else host. */
+int blsgpu_make_sets(blsgpu_ctx *ctx, uint64_t seed, size_t first, size_t n, void *out, int out_on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

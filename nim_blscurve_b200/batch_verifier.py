@@ -1,0 +1,171 @@
+"""Host-side mirror of blscurve/bls_batch_verifier.nim over the C ABI (include/blsgpu.h).
+
+Names, argument meaning and error behaviour follow the reference:
+  * SignatureSet = (pubkey, message, signature)                       bls_batch_verifier.nim:34
+    pubkey 96 B / message 32 B / signature 192 B in the reference's in-memory format.
+  * BatchedBLSVerifierCache.init() / .init(tp)                          :108-119
+  * batchVerifySerial(cache, input, secureRandomBytes)                 :121-160
+  * batchVerifyParallel(tp, cache, input, secureRandomBytes)           :296-397
+  * batchVerify(tp, cache, input, secureRandomBytes)                   :420-495  (parallel iff
+    tp.numThreads > 1 and len >= 3, :440, :468)
+  * aggregateAll(elems) -> (ok, point)                                 blst_min_pubkey_sig_core.nim:179-195
+The Taskpool argument stays in the signatures; it no longer fans work out to threads — its
+numThreads only selects the reference's RLC-scalar chunking so results are identical for a given tp.
+"""
+import ctypes as C
+from typing import NamedTuple, Optional, Sequence
+
+from ._lib import BlsGpuError, lib
+
+
+class SignatureSet(NamedTuple):
+    pubkey: bytes     # 96 B blst_p1_affine
+    message: bytes    # 32 B
+    signature: bytes  # 192 B blst_p2_affine
+
+    def to_bytes(self) -> bytes:
+        assert len(self.pubkey) == 96 and len(self.message) == 32 and len(self.signature) == 192
+        return self.pubkey + self.message + self.signature
+
+
+class Taskpool:
+    """Stand-in for taskpools.Taskpool: only numThreads is consulted (scalar chunking)."""
+
+    def __init__(self, numThreads: int = 1):
+        self.numThreads = int(numThreads)
+
+    @classmethod
+    def new(cls, numThreads: int = 1):
+        return cls(numThreads)
+
+    def shutdown(self):
+        pass
+
+
+def _pack(sets) -> bytes:
+    if isinstance(sets, (bytes, bytearray, memoryview)):
+        b = bytes(sets)
+        assert len(b) % 320 == 0
+        return b
+    return b"".join(s.to_bytes() if isinstance(s, SignatureSet) else SignatureSet(*s).to_bytes() for s in sets)
+
+
+class BatchedBLSVerifierCache:
+    """Device scratch for batch verification (replaces the per-thread pairing contexts, :62-69)."""
+
+    def __init__(self, max_sets: int = 1 << 14, device: int = 0, numThreads: int = 1):
+        L = lib()
+        if L.blsgpu_device_count() <= 0:
+            raise BlsGpuError("no CUDA device visible: nim_blscurve_b200 has no CPU fallback")
+        self._h = L.blsgpu_create(device, max_sets)
+        if not self._h:
+            raise BlsGpuError(L.blsgpu_last_error(None).decode())
+        self.numThreads = numThreads
+        self.device = device
+
+    @classmethod
+    def init(cls, tp: Optional[Taskpool] = None, max_sets: int = 1 << 14, device: int = 0):
+        return cls(max_sets=max_sets, device=device, numThreads=tp.numThreads if tp else 1)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def capacity(self) -> int:
+        return lib().blsgpu_capacity(self._h)
+
+    def last_error(self) -> str:
+        return lib().blsgpu_last_error(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().blsgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- raw calls -------------------------------------------------------------------------
+    def _ensure(self, n):
+        if n > self.capacity():
+            dev = self.device
+            self.close()
+            self.__init__(max_sets=max(n, 1), device=dev, numThreads=self.numThreads)
+
+    def verify_raw(self, sets: bytes, srb: bytes, chunks: int, scalars: Optional[Sequence[int]] = None,
+                   want_gt: bool = False):
+        n = len(sets) // 320
+        self._ensure(n)
+        gt = (C.c_uint8 * 576)() if want_gt else None
+        sc = (C.c_uint64 * n)(*scalars) if scalars is not None else None
+        rc = lib().blsgpu_batch_verify(self._h, sets, n, srb, chunks, sc, gt)
+        if rc < 0:
+            raise BlsGpuError(f"blsgpu_batch_verify failed ({rc}): {self.last_error()}")
+        return (bool(rc), bytes(gt)) if want_gt else bool(rc)
+
+
+def batchVerifySerial(cache: BatchedBLSVerifierCache, input, secureRandomBytes: bytes) -> bool:
+    sets = _pack(input)
+    if len(sets) == 0:
+        return False
+    return cache.verify_raw(sets, secureRandomBytes, 0)
+
+
+def batchVerifyParallel(tp: Taskpool, cache: BatchedBLSVerifierCache, input, secureRandomBytes: bytes) -> bool:
+    sets = _pack(input)
+    if len(sets) == 0:
+        return False
+    return cache.verify_raw(sets, secureRandomBytes, max(1, tp.numThreads))
+
+
+def batchVerify(tp: Taskpool, cache: BatchedBLSVerifierCache, input, secureRandomBytes: bytes) -> bool:
+    sets = _pack(input)
+    n = len(sets) // 320
+    if tp.numThreads > 1 and n >= 3:
+        return batchVerifyParallel(tp, cache, sets, secureRandomBytes)
+    return batchVerifySerial(cache, sets, secureRandomBytes)
+
+
+def aggregateAll(cache: BatchedBLSVerifierCache, elems: Sequence[bytes]):
+    """Sum of public keys (96 B each) or signatures (192 B each) -> (ok, affine point bytes)."""
+    if len(elems) == 0:
+        return False, b""
+    sz = len(elems[0])
+    assert sz in (96, 192) and all(len(e) == sz for e in elems)
+    buf = b"".join(elems)
+    out = (C.c_uint8 * sz)()
+    fn = lib().blsgpu_aggregate_g1 if sz == 96 else lib().blsgpu_aggregate_g2
+    rc = fn(cache.handle, buf, len(elems), out)
+    if rc < 0:
+        raise BlsGpuError(f"aggregate failed ({rc}): {cache.last_error()}")
+    return bool(rc), bytes(out)
+
+
+def hashToG2(cache: BatchedBLSVerifierCache, msgs: bytes, msg_len: int, dst: bytes):
+    """(compressed n*96, affine n*192)"""
+    n = len(msgs) // msg_len if msg_len else 1
+    comp, aff = (C.c_uint8 * (96 * n))(), (C.c_uint8 * (192 * n))()
+    rc = lib().blsgpu_hash_to_g2(cache.handle, msgs if msg_len else None, n, msg_len, dst, len(dst), comp, aff)
+    if rc < 0:
+        raise BlsGpuError(f"hash_to_g2 failed ({rc}): {cache.last_error()}")
+    return bytes(comp), bytes(aff)
+
+
+def msmG1(cache: BatchedBLSVerifierCache, points96: bytes, scalars: bytes, nbits: int = 255) -> bytes:
+    n = len(points96) // 96
+    out = (C.c_uint8 * 96)()
+    rc = lib().blsgpu_msm_g1(cache.handle, points96, scalars, n, nbits, out)
+    if rc < 0:
+        raise BlsGpuError(f"msm_g1 failed ({rc}): {cache.last_error()}")
+    return bytes(out)
+
+
+def rlcScalars(cache: BatchedBLSVerifierCache, srb: bytes, n: int, chunks: int):
+    out = (C.c_uint64 * n)()
+    rc = lib().blsgpu_rlc_scalars(cache.handle, srb, n, chunks, out)
+    if rc < 0:
+        raise BlsGpuError(f"rlc_scalars failed ({rc}): {cache.last_error()}")
+    return list(out)

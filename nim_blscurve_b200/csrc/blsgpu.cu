@@ -1,0 +1,534 @@
+// blsgpu.cu — host side of the C ABI declared in include/blsgpu.h: context, staging, launch sequence.
+// Everything that computes runs in the kernels of kernels.cuh / msm.cuh; this file only moves bytes and
+// launches.  There is no CPU implementation of any operation behind these entry points.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/blsgpu.h"
+#include "kernels.cuh"
+#include "msm.cuh"
+
+using namespace bls;
+
+enum { ST_SCALARS = 0, ST_HASH, ST_G1MUL, ST_AFFINE, ST_G2MUL, ST_G2SUM, ST_MILLER, ST_GTPROD, ST_PARTIAL, ST_FINAL, ST_COUNT };
+static const char *STAGE_NAMES[ST_COUNT] = {"rlc_scalars", "hash_to_g2", "g1_mul64", "pairs_affine", "g2_mul64",
+                                            "g2_sum", "miller_loop", "gt_product", "partial", "final_exp"};
+
+struct blsgpu_ctx {
+    int device = 0;
+    size_t cap = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device buffers
+    sigset *d_sets = nullptr;
+    uint64_t *d_r = nullptr;
+    g2_jac *d_H = nullptr;
+    g1_jac *d_Pj = nullptr;
+    g2_aff *d_Q = nullptr;
+    g1_aff *d_P = nullptr;
+    g2_jac *d_S = nullptr;
+    fp12 *d_F = nullptr;
+    fp12 *d_partials = nullptr;   // 64 slots
+    uint8_t *d_gt = nullptr;      // 576
+    int *d_flags = nullptr;       // [0] pk infinity, [1] is_one
+    void *d_misc = nullptr;       // scratch for aggregate / hash API
+    size_t misc_bytes = 0;
+    uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
+    cudaEvent_t ev[ST_COUNT + 1];
+    bool ev_valid[ST_COUNT + 1];
+    float stage_ms[ST_COUNT];
+    int launches = 0;
+    msm_state msm;
+    std::string err;
+};
+
+static std::string g_err;
+
+static int fail(blsgpu_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    if (c) c->err = buf; else g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return fail(ctx, BLSGPU_ERR_CUDA, #call, e_);      \
+    } while (0)
+
+static inline unsigned nblk(size_t n, unsigned bs = 128) { return (unsigned)((n + bs - 1) / bs); }
+
+extern "C" int blsgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *blsgpu_last_error(const blsgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+extern "C" size_t blsgpu_capacity(const blsgpu_ctx *ctx) { return ctx ? ctx->cap : 0; }
+
+extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_sets); cudaFree(ctx->d_r); cudaFree(ctx->d_H); cudaFree(ctx->d_Pj); cudaFree(ctx->d_Q);
+    cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gt);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_misc);
+    msm_free(ctx->msm);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i <= ST_COUNT; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
+    int ndev = blsgpu_device_count();
+    if (ndev <= 0) { fail(nullptr, 0, "blsgpu_create: no CUDA device (this library has no CPU path)"); return nullptr; }
+    if (device < 0 || device >= ndev) { fail(nullptr, 0, "blsgpu_create: bad device index"); return nullptr; }
+    if (max_sets == 0) max_sets = 1;
+    blsgpu_ctx *ctx = new blsgpu_ctx();
+    ctx->device = device;
+    ctx->cap = max_sets;
+    for (int i = 0; i <= ST_COUNT; i++) ctx->ev_valid[i] = false;
+    for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
+    cudaError_t e = cudaSetDevice(device);
+    auto bad = [&](const char *what, cudaError_t err) {
+        fail(nullptr, 0, what, err);
+        blsgpu_destroy(ctx);
+        return (blsgpu_ctx *)nullptr;
+    };
+    if (e != cudaSuccess) return bad("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
+    ctx->stream = ctx->own_stream;
+    size_t n = max_sets;
+#define ALLOC(ptr, bytes) if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return bad("cudaMalloc " #ptr, e)
+    ALLOC(ctx->d_sets, n * sizeof(sigset));
+    ALLOC(ctx->d_r, n * 8);
+    ALLOC(ctx->d_H, n * sizeof(g2_jac));
+    ALLOC(ctx->d_Pj, n * sizeof(g1_jac));
+    ALLOC(ctx->d_Q, n * sizeof(g2_aff));
+    ALLOC(ctx->d_P, n * sizeof(g1_aff));
+    ALLOC(ctx->d_S, n * sizeof(g2_jac));
+    ALLOC(ctx->d_F, n * sizeof(fp12));
+    ALLOC(ctx->d_partials, 64 * sizeof(fp12));
+    ALLOC(ctx->d_gt, 576);
+    ALLOC(ctx->d_flags, 4 * sizeof(int));
+#undef ALLOC
+    if ((e = cudaMallocHost((void **)&ctx->h_pinned, 4096)) != cudaSuccess) return bad("cudaMallocHost", e);
+    for (int i = 0; i <= ST_COUNT; i++) {
+        if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
+        ctx->ev_valid[i] = true;
+    }
+    return ctx;
+}
+
+extern "C" int blsgpu_set_stream(blsgpu_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return BLSGPU_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+static int ensure_misc(blsgpu_ctx *ctx, size_t bytes) {
+    if (ctx->misc_bytes >= bytes) return 0;
+    if (ctx->d_misc) cudaFree(ctx->d_misc);
+    ctx->d_misc = nullptr;
+    ctx->misc_bytes = 0;
+    CK(cudaMalloc(&ctx->d_misc, bytes));
+    ctx->misc_bytes = bytes;
+    return 0;
+}
+
+static words8 words_of(const uint8_t b[32]) {
+    words8 w;
+    for (int i = 0; i < 8; i++)
+        w.w[i] = ((uint32_t)b[4 * i] << 24) | ((uint32_t)b[4 * i + 1] << 16) | ((uint32_t)b[4 * i + 2] << 8) | b[4 * i + 3];
+    return w;
+}
+
+#define MARK(stage) CK(cudaEventRecord(ctx->ev[stage], s))
+
+// scalars for global indices [first, first+n) into d_r
+static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size_t first, size_t total_n,
+                          uint32_t chunks, const uint64_t *scalars) {
+    cudaStream_t s = ctx->stream;
+    if (scalars) {
+        for (size_t i = 0; i < n; i++) if (scalars[i] == 0) return fail(ctx, BLSGPU_ERR_ARG, "explicit RLC scalar is zero");
+        CK(cudaMemcpyAsync(ctx->d_r, scalars, n * 8, cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+    if (!srb) return fail(ctx, BLSGPU_ERR_ARG, "secureRandomBytes is NULL");
+    size_t nb = chunks == 0 ? 1 : (total_n < chunks ? total_n : (size_t)chunks);
+    k_rlc_scalars<<<nblk(nb, 64), 64, 0, s>>>(words_of(srb), total_n, chunks, first, n, ctx->d_r);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// pairs per Miller-loop thread: share Fp12 squarings when there is parallelism to spare
+static int miller_group(size_t n) { return n >= 65536 ? 4 : (n >= 16384 ? 2 : 1); }
+
+// all per-set stages + reductions; leaves the rank partial in d_partials[slot]
+static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t first, size_t total_n,
+                       const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, int slot) {
+    cudaStream_t s = ctx->stream;
+    ctx->launches = 0;
+    CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
+    MARK(ST_SCALARS);
+    int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars);
+    if (rc) return rc;
+    MARK(ST_HASH);
+    k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+    MARK(ST_G1MUL);
+    k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
+    MARK(ST_AFFINE);
+    k_pairs_affine<<<nblk(n), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P);
+    MARK(ST_G2MUL);
+    k_g2_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_S);
+    ctx->launches += 4;
+    MARK(ST_G2SUM);
+    for (size_t m = n; m > 1;) {
+        size_t half = (m + 1) / 2;
+        k_g2_tree<<<nblk(half), 128, 0, s>>>(ctx->d_S, m, half);
+        ctx->launches++;
+        m = half;
+    }
+    MARK(ST_MILLER);
+    int G = miller_group(n);
+    size_t nf = (n + G - 1) / G;
+    if (G == 4) k_miller<4><<<nblk(nf, 64), 64, 0, s>>>(ctx->d_Q, ctx->d_P, n, ctx->d_F);
+    else if (G == 2) k_miller<2><<<nblk(nf, 64), 64, 0, s>>>(ctx->d_Q, ctx->d_P, n, ctx->d_F);
+    else k_miller<1><<<nblk(nf, 64), 64, 0, s>>>(ctx->d_Q, ctx->d_P, n, ctx->d_F);
+    ctx->launches++;
+    MARK(ST_GTPROD);
+    for (size_t m = nf; m > 1;) {
+        size_t half = (m + 1) / 2;
+        k_fp12_tree<<<nblk(half), 128, 0, s>>>(ctx->d_F, m, half);
+        ctx->launches++;
+        m = half;
+    }
+    MARK(ST_PARTIAL);
+    k_partial<<<1, 32, 0, s>>>(ctx->d_S, ctx->d_F, 1, ctx->d_partials + slot);
+    ctx->launches++;
+    MARK(ST_FINAL);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_inf) {
+    cudaStream_t s = ctx->stream;
+    k_final<<<1, 32, 0, s>>>(ctx->d_partials, count, ctx->d_gt, ctx->d_flags + 1);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[ST_COUNT], s));
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_gt, 576, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_pinned + 576, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int flags[4];
+    memcpy(flags, ctx->h_pinned + 576, sizeof flags);
+    if (pk_inf) *pk_inf = flags[0];
+    if (gt_out) memcpy(gt_out, ctx->h_pinned, 576);
+    return flags[1] ? 1 : 0;
+}
+
+static void collect_stage_times(blsgpu_ctx *ctx, bool with_final) {
+    for (int i = 0; i < ST_COUNT; i++) {
+        float ms = 0.f;
+        if (i == ST_FINAL && !with_final) { ctx->stage_ms[i] = 0.f; continue; }
+        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+        ctx->stage_ms[i] = ms;
+    }
+}
+
+extern "C" int blsgpu_rlc_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, uint32_t chunks, uint64_t *out) {
+    if (!ctx || !out) return BLSGPU_ERR_ARG;
+    if (n == 0) return 0;
+    if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
+    CK(cudaSetDevice(ctx->device));
+    int rc = launch_scalars(ctx, srb, n, 0, n, chunks, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->d_r, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int blsgpu_batch_verify_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n, const uint8_t srb[32],
+                                       uint32_t chunks, const uint64_t *scalars, uint8_t gt_out[576]) {
+    if (!ctx) return BLSGPU_ERR_ARG;
+    if (gt_out) memset(gt_out, 0, 576);
+    if (n == 0) return 0;                                   // bls_batch_verifier.nim:137, :312
+    if (!d_sets) return fail(ctx, BLSGPU_ERR_ARG, "sets is NULL");
+    if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
+    CK(cudaSetDevice(ctx->device));
+    int rc = run_partial(ctx, (const sigset *)d_sets, n, 0, n, srb, chunks, scalars, 0);
+    if (rc) return rc;
+    int pk_inf = 0;
+    rc = run_final(ctx, 1, gt_out, &pk_inf);
+    collect_stage_times(ctx, true);
+    if (rc < 0) return rc;
+    if (pk_inf) { if (gt_out) memset(gt_out, 0, 576); return 0; }   // update() failed -> false (aggregate.c:296)
+    return rc;
+}
+
+extern "C" int blsgpu_batch_verify(blsgpu_ctx *ctx, const void *sets, size_t n, const uint8_t srb[32], uint32_t chunks,
+                                   const uint64_t *scalars, uint8_t gt_out[576]) {
+    if (!ctx) return BLSGPU_ERR_ARG;
+    if (gt_out) memset(gt_out, 0, 576);
+    if (n == 0) return 0;
+    if (!sets) return fail(ctx, BLSGPU_ERR_ARG, "sets is NULL");
+    if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_sets, sets, n * sizeof(sigset), cudaMemcpyHostToDevice, ctx->stream));
+    return blsgpu_batch_verify_dev(ctx, ctx->d_sets, n, srb, chunks, scalars, gt_out);
+}
+
+extern "C" int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_device, size_t n, size_t first,
+                              size_t total_n, const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars,
+                              uint8_t partial_out[576], int *flags) {
+    if (!ctx || !partial_out) return BLSGPU_ERR_ARG;
+    if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "share larger than context capacity");
+    if (first + n > total_n) return fail(ctx, BLSGPU_ERR_ARG, "share outside the batch");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (flags) *flags = 0;
+    if (n == 0) {
+        // an empty share contributes the neutral element: GT one, in the in-memory (Montgomery) layout
+        fp12 one;
+        memset(&one, 0, sizeof one);
+        CK(cudaMemcpyFromSymbol(&one.c0.c0.c0, FP_ONE, sizeof(fp)));
+        memcpy(partial_out, &one, 576);
+        return 0;
+    }
+    const sigset *d = (const sigset *)sets;
+    if (!sets_on_device) {
+        CK(cudaMemcpyAsync(ctx->d_sets, sets, n * sizeof(sigset), cudaMemcpyHostToDevice, s));
+        d = ctx->d_sets;
+    }
+    int rc = run_partial(ctx, d, n, first, total_n, srb, chunks, scalars, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials, 576, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_pinned + 576, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    collect_stage_times(ctx, false);
+    memcpy(partial_out, ctx->h_pinned, 576);
+    int f[4];
+    memcpy(f, ctx->h_pinned + 576, sizeof f);
+    if (flags) *flags = f[0];
+    return 0;
+}
+
+extern "C" int blsgpu_finalize(blsgpu_ctx *ctx, const uint8_t *partials, size_t count, uint8_t gt_out[576]) {
+    if (!ctx || !partials) return BLSGPU_ERR_ARG;
+    if (gt_out) memset(gt_out, 0, 576);
+    if (count == 0) return 0;
+    if (count > 64) return fail(ctx, BLSGPU_ERR_ARG, "at most 64 partials");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    CK(cudaMemcpyAsync(ctx->d_partials, partials, count * 576, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[ST_FINAL], ctx->stream));
+    int rc = run_final(ctx, (int)count, gt_out, nullptr);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[ST_FINAL], ctx->ev[ST_COUNT]) == cudaSuccess) ctx->stage_ms[ST_FINAL] = ms;
+    return rc;
+}
+
+extern "C" int blsgpu_hash_to_g2(blsgpu_ctx *ctx, const uint8_t *msgs, size_t n, size_t msg_len, const uint8_t *dst,
+                                 size_t dst_len, uint8_t *out_compressed, uint8_t *out_affine) {
+    if (!ctx || (!msgs && msg_len) || !dst) return BLSGPU_ERR_ARG;
+    if (dst_len > 255) return fail(ctx, BLSGPU_ERR_ARG, "DST longer than 255 bytes is not supported");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    size_t o_msgs = 0, o_dst = (n * msg_len + 255) & ~(size_t)255, o_aff = o_dst + 256, o_comp = o_aff + n * 192;
+    int rc = ensure_misc(ctx, o_comp + n * 96);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    if (msg_len) CK(cudaMemcpyAsync(base + o_msgs, msgs, n * msg_len, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(base + o_dst, dst, dst_len, cudaMemcpyHostToDevice, s));
+    k_hash_to_g2<<<nblk(n), 128, 0, s>>>(base + o_msgs, n, msg_len, base + o_dst, (uint32_t)dst_len,
+                                         out_affine ? (g2_aff *)(base + o_aff) : nullptr, out_compressed ? base + o_comp : nullptr);
+    CK(cudaGetLastError());
+    if (out_affine) CK(cudaMemcpyAsync(out_affine, base + o_aff, n * 192, cudaMemcpyDeviceToHost, s));
+    if (out_compressed) CK(cudaMemcpyAsync(out_compressed, base + o_comp, n * 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int blsgpu_debug_h2c(blsgpu_ctx *ctx, const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, void *out) {
+    if (!ctx) return BLSGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_misc(ctx, 4096 + sizeof(h2c_trace) + msg_len);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(base, dst, dst_len, cudaMemcpyHostToDevice, s));
+    if (msg_len) CK(cudaMemcpyAsync(base + 256, msg, msg_len, cudaMemcpyHostToDevice, s));
+    h2c_trace *t = (h2c_trace *)(base + 256 + ((msg_len + 255) & ~(size_t)255));
+    k_h2c_trace<<<1, 32, 0, s>>>(base + 256, msg_len, base, (uint32_t)dst_len, t);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, t, sizeof(h2c_trace), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return (int)sizeof(h2c_trace);
+}
+
+extern "C" int blsgpu_debug2(blsgpu_ctx *ctx, const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, void *out) {
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_misc(ctx, 8192 + msg_len);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(base, dst, dst_len, cudaMemcpyHostToDevice, s));
+    if (msg_len) CK(cudaMemcpyAsync(base + 256, msg, msg_len, cudaMemcpyHostToDevice, s));
+    uint8_t *o = base + 256 + ((msg_len + 255) & ~(size_t)255);
+    k_dbg2<<<1, 128, 0, s>>>(base + 256, 1, msg_len, base, (uint32_t)dst_len, (g2_jac *)o, (g2_aff *)(o + 288));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, o, 480, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 480;
+}
+
+extern "C" int blsgpu_aggregate_g1(blsgpu_ctx *ctx, const void *points96, size_t n, uint8_t out96[96]) {
+    if (!ctx || !out96) return BLSGPU_ERR_ARG;
+    if (n == 0) return 0;                                   // blst_min_pubkey_sig_core.nim:183-184
+    if (!points96) return BLSGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int rc = ensure_misc(ctx, n * (sizeof(g1_aff) + sizeof(g1_jac)) + 256);
+    if (rc) return rc;
+    g1_jac *J = (g1_jac *)ctx->d_misc;
+    g1_aff *A = (g1_aff *)((uint8_t *)ctx->d_misc + n * sizeof(g1_jac));
+    CK(cudaMemcpyAsync(A, points96, n * sizeof(g1_aff), cudaMemcpyHostToDevice, s));
+    k_g1_load<<<nblk(n), 128, 0, s>>>(A, n, J);
+    for (size_t m = n; m > 1;) { size_t half = (m + 1) / 2; k_g1_tree<<<nblk(half), 128, 0, s>>>(J, m, half); m = half; }
+    k_g1_to_affine<<<1, 32, 0, s>>>(J, A);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out96, A, 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 1;
+}
+
+extern "C" int blsgpu_aggregate_g2(blsgpu_ctx *ctx, const void *points192, size_t n, uint8_t out192[192]) {
+    if (!ctx || !out192) return BLSGPU_ERR_ARG;
+    if (n == 0) return 0;
+    if (!points192) return BLSGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int rc = ensure_misc(ctx, n * (sizeof(g2_aff) + sizeof(g2_jac)) + 256);
+    if (rc) return rc;
+    g2_jac *J = (g2_jac *)ctx->d_misc;
+    g2_aff *A = (g2_aff *)((uint8_t *)ctx->d_misc + n * sizeof(g2_jac));
+    CK(cudaMemcpyAsync(A, points192, n * sizeof(g2_aff), cudaMemcpyHostToDevice, s));
+    k_g2_load<<<nblk(n), 128, 0, s>>>(A, n, J);
+    for (size_t m = n; m > 1;) { size_t half = (m + 1) / 2; k_g2_tree<<<nblk(half), 128, 0, s>>>(J, m, half); m = half; }
+    k_g2_to_affine<<<1, 32, 0, s>>>(J, A);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out192, A, 192, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 1;
+}
+
+extern "C" int blsgpu_msm_g1_dev(blsgpu_ctx *ctx, const void *d_points96, const void *d_scalars, size_t n, size_t nbits,
+                                 uint8_t out96[96]) {
+    if (!ctx || !out96) return BLSGPU_ERR_ARG;
+    memset(out96, 0, 96);
+    if (n == 0) return 0;
+    if (!d_points96 || !d_scalars || nbits == 0 || nbits > 256) return fail(ctx, BLSGPU_ERR_ARG, "bad MSM arguments");
+    CK(cudaSetDevice(ctx->device));
+    std::string err;
+    int rc = msm_g1_run(ctx->msm, (const g1_aff *)d_points96, (const uint8_t *)d_scalars, n, (int)nbits, ctx->stream,
+                        ctx->h_pinned, err);
+    if (rc) return fail(ctx, rc, err.c_str());
+    memcpy(out96, ctx->h_pinned, 96);
+    return 1;
+}
+
+extern "C" int blsgpu_msm_g1(blsgpu_ctx *ctx, const void *points96, const void *scalars, size_t n, size_t nbits,
+                             uint8_t out96[96]) {
+    if (!ctx || !out96) return BLSGPU_ERR_ARG;
+    memset(out96, 0, 96);
+    if (n == 0) return 0;
+    if (!points96 || !scalars || nbits == 0 || nbits > 256) return fail(ctx, BLSGPU_ERR_ARG, "bad MSM arguments");
+    CK(cudaSetDevice(ctx->device));
+    size_t sb = (nbits + 7) / 8;
+    int rc = ensure_misc(ctx, n * 96 + n * sb + 256);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    CK(cudaMemcpyAsync(base, points96, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(base + n * 96, scalars, n * sb, cudaMemcpyHostToDevice, ctx->stream));
+    return blsgpu_msm_g1_dev(ctx, base, base + n * 96, n, nbits, out96);
+}
+
+extern "C" int blsgpu_last_stage_ms(const blsgpu_ctx *ctx, float *ms, int max) {
+    if (!ctx || !ms) return 0;
+    int k = max < ST_COUNT ? max : ST_COUNT;
+    for (int i = 0; i < k; i++) ms[i] = ctx->stage_ms[i];
+    return k;
+}
+extern "C" const char *blsgpu_stage_name(int stage) { return stage >= 0 && stage < ST_COUNT ? STAGE_NAMES[stage] : ""; }
+extern "C" int blsgpu_last_launches(const blsgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int blsgpu_test_fp(blsgpu_ctx *ctx, int op, const void *a, const void *b, size_t n, void *out) {
+    if (!ctx || !a || !out) return BLSGPU_ERR_ARG;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_misc(ctx, 3 * n * 48);
+    if (rc) return rc;
+    fp *da = (fp *)ctx->d_misc, *db = da + n, *dout = db + n;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(da, a, n * 48, cudaMemcpyHostToDevice, s));
+    if (b) CK(cudaMemcpyAsync(db, b, n * 48, cudaMemcpyHostToDevice, s));
+    k_test_fp<<<nblk(n), 128, 0, s>>>(op, da, b ? db : nullptr, n, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, n * 48, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" double blsgpu_imad_peak(blsgpu_ctx *ctx, int wide) {
+    if (!ctx) return -1.0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
+    if (ensure_misc(ctx, 256)) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return -1.0;
+    const int iters = 4096, blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaStream_t s = ctx->stream;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, s);
+        if (wide) k_imad_peak<1><<<blocks, threads, 0, s>>>((uint32_t *)ctx->d_misc, iters, 12345u + rep);
+        else k_imad_peak<0><<<blocks, threads, 0, s>>>((uint32_t *)ctx->d_misc, iters, 12345u + rep);
+        cudaEventRecord(e1, s);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double ops = (double)blocks * threads * iters * 64.0;
+        double rate = ops / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+}
+
+extern "C" int blsgpu_make_sets(blsgpu_ctx *ctx, uint64_t seed, size_t first, size_t n, void *out, int out_on_device) {
+    if (!ctx || !out) return BLSGPU_ERR_ARG;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    sigset *d = (sigset *)out;
+    if (!out_on_device) {
+        if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
+        d = ctx->d_sets;
+    }
+    uint8_t sb[32] = {0};
+    memcpy(sb, &seed, 8);
+    k_make_sets<<<nblk(n), 128, 0, s>>>(words_of(sb), first, n, d);
+    CK(cudaGetLastError());
+    if (!out_on_device) CK(cudaMemcpyAsync(out, d, n * sizeof(sigset), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}

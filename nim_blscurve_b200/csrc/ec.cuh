@@ -54,7 +54,7 @@ template <class F> BLS_FN void pt_from_affine(jac_t<F> &r, const aff_t<F> &a) {
 template <class F> BLS_FN void pt_neg(jac_t<F> &r, const jac_t<F> &a) { r.x = a.x; f_neg(r.y, a.y); r.z = a.z; }
 
 // dbl-2009-l (a = 0): 2M + 5S.  Infinity (Z=0) and order-2 points (Y=0) map to Z3 = 0.
-template <class F> BLS_FN void pt_dbl(jac_t<F> &r, const jac_t<F> &p) {
+template <class F> BLS_NOINLINE void pt_dbl(jac_t<F> &r, const jac_t<F> &p) {
     F A, B, C, D, E, Fq, t;
     f_sqr(A, p.x);
     f_sqr(B, p.y);
@@ -81,7 +81,7 @@ template <class F> BLS_FN void pt_dbl(jac_t<F> &r, const jac_t<F> &p) {
 }
 
 // general doubling with curve coefficient a (dbl-2007-bl); only used for the E2' corner case
-template <class F> BLS_FN void pt_dbl_a(jac_t<F> &r, const jac_t<F> &p, const F &a) {
+template <class F> BLS_NOINLINE void pt_dbl_a(jac_t<F> &r, const jac_t<F> &p, const F &a) {
     F XX, YY, YYYY, ZZ, S, M, T, t;
     f_sqr(XX, p.x);
     f_sqr(YY, p.y);
@@ -115,7 +115,7 @@ template <class F> BLS_FN void pt_dbl_a(jac_t<F> &r, const jac_t<F> &p, const F 
 
 // add-2007-bl: 11M + 5S, complete by case analysis.  `a_coeff` (nullable) is only consulted when
 // the inputs turn out to be equal and the curve is not a=0 (hash-to-curve adds on E2').
-template <class F> BLS_FN void pt_add(jac_t<F> &r, const jac_t<F> &p, const jac_t<F> &q, const F *a_coeff = nullptr) {
+template <class F> BLS_NOINLINE void pt_add(jac_t<F> &r, const jac_t<F> &p, const jac_t<F> &q, const F *a_coeff = nullptr) {
     if (pt_is_inf(p)) { r = q; return; }
     if (pt_is_inf(q)) { r = p; return; }
     F Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t;
@@ -160,7 +160,7 @@ template <class F> BLS_FN void pt_add(jac_t<F> &r, const jac_t<F> &p, const jac_
 }
 
 // madd-2007-bl: 7M + 4S, q affine (all-zero = infinity)
-template <class F> BLS_FN void pt_add_affine(jac_t<F> &r, const jac_t<F> &p, const aff_t<F> &q) {
+template <class F> BLS_NOINLINE void pt_add_affine(jac_t<F> &r, const jac_t<F> &p, const aff_t<F> &q) {
     if (aff_is_inf(q)) { r = p; return; }
     if (pt_is_inf(p)) { pt_from_affine(r, q); return; }
     F Z1Z1, U2, S2, H, HH, I, J, rr, V, t;
@@ -198,7 +198,7 @@ template <class F> BLS_FN void pt_add_affine(jac_t<F> &r, const jac_t<F> &p, con
 }
 
 // affine from Jacobian (infinity -> all zero)
-template <class F> BLS_FN void pt_to_affine(aff_t<F> &r, const jac_t<F> &p) {
+template <class F> BLS_NOINLINE void pt_to_affine(aff_t<F> &r, const jac_t<F> &p) {
     if (pt_is_inf(p)) { f_set_zero(r.x); f_set_zero(r.y); return; }
     F zi, zi2;
     f_inv(zi, p.z);
@@ -209,7 +209,7 @@ template <class F> BLS_FN void pt_to_affine(aff_t<F> &r, const jac_t<F> &p) {
 }
 
 // same, with 1/Z supplied (batch inversion)
-template <class F> BLS_FN void pt_to_affine_zinv(aff_t<F> &r, const jac_t<F> &p, const F &zi) {
+template <class F> BLS_NOINLINE void pt_to_affine_zinv(aff_t<F> &r, const jac_t<F> &p, const F &zi) {
     if (pt_is_inf(p)) { f_set_zero(r.x); f_set_zero(r.y); return; }
     F zi2;
     f_sqr(zi2, zi);
@@ -220,7 +220,7 @@ template <class F> BLS_FN void pt_to_affine_zinv(aff_t<F> &r, const jac_t<F> &p,
 
 // r = [k]P for a 64-bit k, P affine: MSB-first double-and-add with mixed additions.
 // (BLST uses a 5-bit Booth window, ec_mult.h:178-223; the affine result is the same point.)
-template <class F> BLS_FN void pt_mul_u64(jac_t<F> &r, const aff_t<F> &p, uint64_t k) {
+template <class F> BLS_NOINLINE void pt_mul_u64(jac_t<F> &r, const aff_t<F> &p, uint64_t k) {
     jac_t<F> acc;
     pt_set_inf(acc);
     if (k != 0 && !aff_is_inf(p)) {
@@ -236,7 +236,7 @@ template <class F> BLS_FN void pt_mul_u64(jac_t<F> &r, const aff_t<F> &p, uint64
 }
 
 // r = [k]P, P Jacobian, k given as nwords little-endian u32 words (top bit need not be set)
-template <class F> BLS_FN void pt_mul_words(jac_t<F> &r, const jac_t<F> &p, const uint32_t *k, int nwords) {
+template <class F> BLS_NOINLINE void pt_mul_words(jac_t<F> &r, const jac_t<F> &p, const uint32_t *k, int nwords) {
     jac_t<F> acc;
     pt_set_inf(acc);
     for (int i = nwords * 32 - 1; i >= 0; i--) {

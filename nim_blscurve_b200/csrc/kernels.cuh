@@ -1,0 +1,390 @@
+// kernels.cuh — __global__ kernels of the batch-verification pipeline (one signature set per thread).
+//
+// Stage order (blsgpu.cu launches them on one stream):
+//   k_rlc_scalars   A2  blst_min_pubkey_sig_core.nim:476-505,:545-556   one thread per reference chunk
+//   k_hash_sets     A3  map_to_g2.c:388-396                               H(m_i), Jacobian
+//   k_g1_mul        A5  ec_mult.h:178-223 (G1)                            [r_i] pk_i, Jacobian
+//   k_pairs_affine  A4  e2.c:97-112, e1.c:60-75                           one shared inversion per set
+//   k_g2_mul        A5  ec_mult.h:178-223 (G2)                            [r_i] sig_i ; k_g2_tree sums them
+//   k_miller<G>     A6/A7 pairing.c:220-261                               G pairs per thread share squarings
+//   k_fp12_tree     A8  aggregate.c:410-458 (GT product)
+//   k_partial       A9  aggregate.c:479-495                               conj(ML(S,G1)) * F  -> 576-byte partial
+//   k_final         A9/A10 pairing.c:371-404, fp12_tower.c:773-786        product, final exp, ==1, GT bytes
+#pragma once
+#include <cuda_runtime.h>
+#include "h2c.cuh"
+#include "pairing.cuh"
+
+namespace bls {
+
+struct sigset { g1_aff pk; uint8_t msg[32]; g2_aff sig; };
+static_assert(sizeof(sigset) == 320, "SignatureSet layout (bls_batch_verifier.nim:34)");
+static_assert(sizeof(fp12) == 576 && sizeof(g2_jac) == 288 && sizeof(g1_jac) == 144, "layout");
+
+// blscurve/bls_sig_min_pubkey.nim:31
+__device__ __constant__ const uint8_t DST_ETH2[43] = {
+    'B','L','S','_','S','I','G','_','B','L','S','1','2','3','8','1','G','2','_','X','M','D',':','S','H','A','-',
+    '2','5','6','_','S','S','W','U','_','R','O','_','P','O','P','_'};
+
+struct words8 { uint32_t w[8]; };   // a 32-byte string as big-endian words
+
+// SHA-256 of a 32-byte input held as BE words (one compression)
+__device__ __forceinline__ void sha256_of_32(uint32_t *out, const uint32_t *in) {
+    uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    uint32_t w[16];
+    for (int i = 0; i < 8; i++) w[i] = in[i];
+    w[8] = 0x80000000u;
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = 256;
+    sha256_block(h, w);
+    for (int i = 0; i < 8; i++) out[i] = h[i];
+}
+
+__device__ __forceinline__ uint64_t le64_of_be_words(const uint32_t *d) {
+    // first 8 bytes of the digest read as a little-endian u64
+    uint32_t lo = __byte_perm(d[0], 0, 0x0123), hi = __byte_perm(d[1], 0, 0x0123);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void chunk_range(size_t nchunks, size_t total, size_t cid, size_t &off, size_t &len) {
+    size_t base = total / nchunks, rem = total % nchunks;
+    if (cid < rem) { off = (base + 1) * cid; len = base + 1; }
+    else { off = base * cid + rem; len = base; }
+}
+
+// One thread per reference chunk walks that chunk's sequential SHA-256 chain and stores the scalars of
+// the indices this rank owns ([first, first+n) of the global batch).
+__global__ void k_rlc_scalars(words8 srb, size_t total_n, uint32_t chunks, size_t first, size_t n, uint64_t *out) {
+    size_t nb = chunks == 0 ? 1 : (total_n < chunks ? total_n : (size_t)chunks);
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nb) return;
+    size_t off, len;
+    chunk_range(nb, total_n, c, off, len);
+    if (off >= first + n || off + len <= first) return;
+    uint32_t seed[8];
+    if (chunks == 0) {
+        sha256_of_32(seed, srb.w);
+    } else {                                           // SHA256(srb || LE64(c)): 40 bytes, one block
+        uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        uint32_t w[16];
+        for (int i = 0; i < 8; i++) w[i] = srb.w[i];
+        w[8] = __byte_perm((uint32_t)c, 0, 0x0123);
+        w[9] = __byte_perm((uint32_t)((uint64_t)c >> 32), 0, 0x0123);
+        w[10] = 0x80000000u;
+        for (int i = 11; i < 15; i++) w[i] = 0;
+        w[15] = 320;
+        sha256_block(h, w);
+        for (int i = 0; i < 8; i++) seed[i] = h[i];
+    }
+    for (size_t i = off; i < off + len; i++) {
+        uint64_t r;
+        do {
+            uint32_t t[8];
+            sha256_of_32(t, seed);
+            for (int k = 0; k < 8; k++) seed[k] = t[k];
+            r = le64_of_be_words(seed);
+        } while (r == 0);
+        if (i >= first && i < first + n) out[i - first] = r;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_hash_sets(const sigset *sets, size_t n, g2_jac *H) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t msg[32], dst[43];
+    for (int k = 0; k < 32; k++) msg[k] = sets[i].msg[k];
+    for (int k = 0; k < 43; k++) dst[k] = DST_ETH2[k];
+    g2_jac h;
+    hash_to_g2_jac(h, msg, 32, dst, 43);
+    H[i] = h;
+}
+
+__global__ void __launch_bounds__(128) k_g1_mul(const sigset *sets, const uint64_t *r, size_t n, g1_jac *Pj, int *flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_aff pk = sets[i].pk;
+    if (aff_is_inf(pk)) atomicOr(flags, 1);            // BLST_PK_IS_INFINITY (aggregate.c:296)
+    g1_jac j;
+    pt_mul_u64(j, pk, r[i]);
+    Pj[i] = j;
+}
+
+// H_i and [r_i]pk_i to affine with ONE Fermat inversion per set (Montgomery's trick on N(Z_H) and Z_P)
+__global__ void __launch_bounds__(128) k_pairs_affine(const g2_jac *H, const g1_jac *Pj, size_t n, g2_aff *Q, g1_aff *P) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_jac h = H[i];
+    g1_jac p = Pj[i];
+    fp nz, t, zp = p.z, prod, inv, ninv, zpinv;
+    fp_sqr_ni(nz, h.z.c0);
+    fp_sqr_ni(t, h.z.c1);
+    fp_add(nz, nz, t);                                  // N(Z_H)
+    bool h_inf = fp_is_zero(nz), p_inf = fp_is_zero(zp);
+    if (h_inf) nz = FP_ONE;
+    if (p_inf) zp = FP_ONE;
+    fp_mul_ni(prod, nz, zp);
+    fp_inv(inv, prod);
+    fp_mul_ni(ninv, inv, zp);                           // 1/N(Z_H)
+    fp_mul_ni(zpinv, inv, nz);                          // 1/Z_P
+    fp2 zhinv;
+    fp_mul_ni(zhinv.c0, h.z.c0, ninv);
+    fp_mul_ni(t, h.z.c1, ninv);
+    fp_neg(zhinv.c1, t);
+    g2_aff q;
+    g1_aff a;
+    pt_to_affine_zinv(q, h, zhinv);
+    pt_to_affine_zinv(a, p, zpinv);
+    Q[i] = q;
+    P[i] = a;
+}
+
+__global__ void __launch_bounds__(128) k_g2_mul(const sigset *sets, const uint64_t *r, size_t n, g2_jac *S) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_aff sig = sets[i].sig;
+    g2_jac j;
+    pt_mul_u64(j, sig, r[i]);                           // infinite signature contributes nothing (aggregate.c:261)
+    S[i] = j;
+}
+
+// pairwise tree step: x[i] (op)= x[i + half] for i + half < n
+__global__ void __launch_bounds__(128) k_g2_tree(g2_jac *S, size_t n, size_t half) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half || i + half >= n) return;
+    g2_jac a = S[i], b = S[i + half];
+    pt_add(a, a, b);
+    S[i] = a;
+}
+
+__global__ void __launch_bounds__(128) k_g1_tree(g1_jac *S, size_t n, size_t half) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half || i + half >= n) return;
+    g1_jac a = S[i], b = S[i + half];
+    pt_add(a, a, b);
+    S[i] = a;
+}
+
+__global__ void __launch_bounds__(128) k_fp12_tree(fp12 *F, size_t n, size_t half) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half || i + half >= n) return;
+    fp12 a = F[i], b = F[i + half];
+    fp12_mul(a, a, b);
+    F[i] = a;
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) k_miller(const g2_aff *Q, const g1_aff *P, size_t n, fp12 *F) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t base = t * G;
+    if (base >= n) return;
+    int cnt = (n - base) < (size_t)G ? (int)(n - base) : G;
+    g2_aff q[G];
+    g1_aff p[G];
+    g2_jac T[G];
+    fp npx[G];
+    for (int k = 0; k < cnt; k++) { q[k] = Q[base + k]; p[k] = P[base + k]; }
+    fp12 f;
+    miller_loop_n(f, q, p, cnt, T, npx);
+    F[t] = f;
+}
+
+// conj(ML(S, G1)) * F  (aggregate.c:479-495); single thread
+__global__ void k_partial(const g2_jac *S, const fp12 *F, int have_sets, fp12 *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    g2_jac s = *S;
+    g2_aff sa;
+    pt_to_affine(sa, s);
+    g1_aff g;
+    g.x = G1_GEN_X;
+    g.y = G1_GEN_Y;
+    fp12 gs, f;
+    g2_jac T[1];
+    fp npx[1];
+    miller_loop_n(gs, &sa, &g, 1, T, npx);              // S = infinity -> one (aggregate.c:486-492, pairing.c:233-241)
+    fp12_conj(gs, gs);
+    if (have_sets) { f = *F; fp12_mul(gs, gs, f); }
+    *out = gs;
+}
+
+// prod partials -> final exponentiation -> (== 1), canonical GT bytes
+__global__ void k_final(const fp12 *partials, int count, uint8_t *gt_bytes, int *is_one) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    fp12 acc = partials[0];
+    for (int i = 1; i < count; i++) { fp12 b = partials[i]; fp12_mul(acc, acc, b); }
+    fp12 gt;
+    final_exp(gt, acc);
+    *is_one = fp12_is_one(gt) ? 1 : 0;
+    fp12_to_bytes(gt_bytes, gt);
+}
+
+// ---- generic hash_to_G2 entry (arbitrary message length and DST, both in global memory) ----
+__global__ void __launch_bounds__(128) k_hash_to_g2(const uint8_t *msgs, size_t n, size_t msg_len, const uint8_t *dst,
+                                                    uint32_t dst_len, g2_aff *out_aff, uint8_t *out_comp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_jac h;
+    hash_to_g2_jac(h, msgs + i * msg_len, msg_len, dst, dst_len);
+    g2_aff a;
+    pt_to_affine(a, h);
+    if (out_aff) out_aff[i] = a;
+    if (out_comp) g2_compress(out_comp + 96 * i, a);
+}
+
+// stage-by-stage dump of hash_to_G2 for debugging: u0,u1 | q0 | q1 | q0+q1 | iso | cleared (Jacobian) | affine
+struct h2c_trace { fp2 u0, u1; g2_jac q0, q1, sum, iso, out; g2_aff aff; g2_jac alt; g2_aff alt_aff; };
+__device__ __forceinline__ void h2c_trace_run(h2c_trace &t, const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len) {
+    hash_to_field_fp2x2(t.u0, t.u1, msg, msg_len, dst, dst_len);
+    sswu_g2(t.q0, t.u0);
+    sswu_g2(t.q1, t.u1);
+    pt_add(t.sum, t.q0, t.q1, &SSWU_A);
+    iso3_g2(t.iso, t.sum);
+    g2_clear_cofactor(t.out, t.iso);
+    pt_to_affine(t.aff, t.out);
+    hash_to_g2_jac(t.alt, msg, msg_len, dst, dst_len);
+    pt_to_affine(t.alt_aff, t.alt);
+}
+__global__ void k_h2c_trace(const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len, h2c_trace *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    h2c_trace t;
+    h2c_trace_run(t, msg, msg_len, dst, dst_len);
+    *out = t;
+}
+
+__global__ void __launch_bounds__(128) k_dbg2(const uint8_t *msgs, size_t n, size_t msg_len, const uint8_t *dst,
+                                              uint32_t dst_len, g2_jac *out_jac, g2_aff *out_aff) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_jac h;
+    hash_to_g2_jac(h, msgs + i * msg_len, msg_len, dst, dst_len);
+    out_jac[i] = h;
+    g2_aff a;
+    pt_to_affine(a, h);
+    out_aff[i] = a;
+}
+// ---- aggregateAll helpers ----
+__global__ void __launch_bounds__(128) k_g1_load(const g1_aff *in, size_t n, g1_jac *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_aff a = in[i];
+    g1_jac j;
+    pt_from_affine(j, a);
+    out[i] = j;
+}
+__global__ void __launch_bounds__(128) k_g2_load(const g2_aff *in, size_t n, g2_jac *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_aff a = in[i];
+    g2_jac j;
+    pt_from_affine(j, a);
+    out[i] = j;
+}
+__global__ void k_g1_to_affine(const g1_jac *in, g1_aff *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    g1_jac j = *in;
+    g1_aff a;
+    pt_to_affine(a, j);
+    *out = a;
+}
+__global__ void k_g2_to_affine(const g2_jac *in, g2_aff *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    g2_jac j = *in;
+    g2_aff a;
+    pt_to_affine(a, j);
+    *out = a;
+}
+
+// ---- diagnostics ----
+__global__ void k_test_fp(int op, const fp *a, const fp *b, size_t n, fp *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp x = a[i], y, r;
+    if (b) y = b[i]; else y = x;
+    switch (op) {
+        case 0: fp_mul(r, x, y); break;
+        case 1: fp_add(r, x, y); break;
+        case 2: fp_sub(r, x, y); break;
+        case 3: fp_sqr(r, x); break;
+        default: fp_inv(r, x); break;
+    }
+    out[i] = r;
+}
+
+// Integer-multiply pipe peak: 8 independent mad.wide (or mad.lo) chains per thread, no memory traffic.
+template <int WIDE>
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters, uint32_t seed) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    if (WIDE) {
+        uint64_t acc[8];
+        for (int k = 0; k < 8; k++) acc[k] = k;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b + u));
+            }
+        }
+        uint64_t s = 0;
+        for (int k = 0; k < 8; k++) s ^= acc[k];
+        if (s == 0x1234567) sink[0] = (uint32_t)s;
+    } else {
+        uint32_t acc[8];
+        for (int k = 0; k < 8; k++) acc[k] = k;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a + k), "r"(b + u));
+            }
+        }
+        uint32_t s = 0;
+        for (int k = 0; k < 8; k++) s ^= acc[k];
+        if (s == 0x1234567) sink[0] = s;
+    }
+}
+
+// Synthetic valid signature sets, generated on the device (benchmark input only).
+__global__ void __launch_bounds__(128) k_make_sets(words8 seed, size_t first, size_t n, sigset *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t idx = first + i;
+    // sk = 1 + (SHA256(seed || LE64(idx)) mod 2^250)
+    uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    uint32_t w[16];
+    for (int k = 0; k < 8; k++) w[k] = seed.w[k];
+    w[8] = __byte_perm((uint32_t)idx, 0, 0x0123);
+    w[9] = __byte_perm((uint32_t)(idx >> 32), 0, 0x0123);
+    w[10] = 0x80000000u;
+    for (int k = 11; k < 15; k++) w[k] = 0;
+    w[15] = 320;
+    sha256_block(h, w);
+    uint32_t sk[8];
+    for (int k = 0; k < 8; k++) sk[k] = h[7 - k];
+    sk[7] &= 0x03ffffffu;
+    sk[0] |= 1;                                         // non-zero
+    // msg = SHA256("blsgpu" || LE64(idx))
+    uint8_t pre[14] = {'b', 'l', 's', 'g', 'p', 'u'};
+    for (int k = 0; k < 8; k++) pre[6 + k] = (uint8_t)(idx >> (8 * k));
+    sha256_ctx c;
+    sha256_init(c);
+    sha256_update(c, pre, 14);
+    uint32_t md[8];
+    sha256_final(c, md);
+    uint8_t msg[32], dst[43];
+    for (int k = 0; k < 32; k++) msg[k] = (uint8_t)(md[k >> 2] >> (24 - 8 * (k & 3)));
+    for (int k = 0; k < 43; k++) dst[k] = DST_ETH2[k];
+    g1_jac g, pkj;
+    g.x = G1_GEN_X; g.y = G1_GEN_Y; g.z = FP_ONE;
+    pt_mul_words(pkj, g, sk, 8);
+    g2_jac hj, sj;
+    hash_to_g2_jac(hj, msg, 32, dst, 43);
+    pt_mul_words(sj, hj, sk, 8);
+    sigset s;
+    pt_to_affine(s.pk, pkj);
+    pt_to_affine(s.sig, sj);
+    for (int k = 0; k < 32; k++) s.msg[k] = msg[k];
+    out[i] = s;
+}
+
+}  // namespace bls

@@ -1,0 +1,139 @@
+"""GPU parity: batch verification through the C ABI vs BLST (oracle/_ref) on the scenarios of
+/root/reference/tests/t_batch_verifier.nim — verify boolean AND the 576-byte GT must match."""
+import hashlib
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def both(cache, br, sets, srb, chunks, scalars=None):
+    ok, gt = cache.verify_raw(sets, srb, chunks, scalars=scalars, want_gt=True)
+    rok, rgt = br.batch_verify(sets, srb, chunks, scalars=scalars)
+    assert ok == rok
+    assert gt == rgt
+    return ok
+
+
+def examples(br, n):
+    # addExample(i, "msg" & $i)  (t_batch_verifier.nim:42-47)
+    return br.make_sets(0, n, b"msg")
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17])
+@pytest.mark.parametrize("chunks", [0, 4])
+def test_valid_batches(cache, br, srb, n, chunks):
+    assert both(cache, br, examples(br, n), srb, chunks) is True
+
+
+@pytest.mark.parametrize("chunks", [0, 4])
+def test_wrong_signature(cache, br, srb, chunks):
+    s1 = br.make_set(1, b"msg1")
+    s2 = br.make_set(2, b"msg2")
+    bad = s1 + s2[:128] + s1[128:]          # (pubkey2, msg2, sig1)   t_batch_verifier.nim:122-137
+    assert both(cache, br, bad, srb, chunks) is False
+
+
+def forged_pair(br, cache, seed1, m1, seed2, m2):
+    """S1+S', S2-S' (t_batch_verifier.nim:198-244)."""
+    import nim_blscurve_b200 as bg
+    a, b = br.make_set(seed1, m1), br.make_set(seed2, m2)
+    p = br.make_set(seed1 * seed2 + seed1 + seed2, b"rekt")
+    sp = p[128:]
+    nsp = br.g2_neg(sp)
+    ok1, f1 = br.aggregate_g2(a[128:] + sp)
+    ok2, f2 = br.aggregate_g2(b[128:] + nsp)
+    assert ok1 and ok2
+    # the same aggregation on the GPU must give the same points
+    g1 = bg.aggregateAll(cache, [a[128:], sp])
+    g2 = bg.aggregateAll(cache, [b[128:], nsp])
+    assert g1 == (True, f1) and g2 == (True, f2)
+    return a[:128] + f1 + b[:128] + f2
+
+
+@pytest.mark.parametrize("chunks", [0, 4])
+def test_forged_pair(cache, br, srb, chunks):
+    batch = forged_pair(br, cache, 1, b"msg1", 2, b"msg2")
+    assert both(cache, br, batch, srb, chunks) is False
+
+
+@pytest.mark.parametrize("chunks", [0, 4])
+def test_one_forgery_among_many(cache, br, srb, chunks):
+    sets = examples(br, 16) + forged_pair(br, cache, 1, b"msg100", 2, b"msg200")
+    items = [sets[i:i + 320] for i in range(0, len(sets), 320)]
+    random.Random(1234).shuffle(items)
+    assert both(cache, br, b"".join(items), srb, chunks) is False
+
+
+def test_same_message_100(cache, br, srb):
+    msg = hashlib.sha256(b"msg").digest()
+    sets = b"".join(br.sign_hashed(i, msg) for i in range(100))
+    assert both(cache, br, sets, srb, 4) is True
+
+
+def test_empty_is_false(cache, srb):
+    assert cache.verify_raw(b"", srb, 0) is False
+    import nim_blscurve_b200 as bg
+    assert bg.batchVerify(bg.Taskpool.new(4), cache, [], srb) is False
+
+
+def test_infinite_pubkey_fails(cache, br, srb):
+    sets = bytearray(examples(br, 5))
+    sets[2 * 320:2 * 320 + 96] = bytes(96)
+    sets[2 * 320 + 128:3 * 320] = bytes(192)        # infinite pk AND infinite sig still fails (aggregate.c:296)
+    ok, gt = cache.verify_raw(bytes(sets), srb, 0, want_gt=True)
+    rok, _ = br.batch_verify(bytes(sets), srb, 0)
+    assert ok is False and rok is False
+
+
+def test_infinite_signature_is_skipped(cache, br, srb):
+    sets = bytearray(examples(br, 4))
+    sets[320 + 128:640] = bytes(192)
+    assert both(cache, br, bytes(sets), srb, 0) is False
+    # all signatures infinite: GTsig := one (aggregate.c:486-492)
+    for i in range(4):
+        sets[i * 320 + 128:(i + 1) * 320] = bytes(192)
+    assert both(cache, br, bytes(sets), srb, 4) is False
+
+
+def test_explicit_scalars(cache, br, srb):
+    sets = examples(br, 9)
+    sc = [random.Random(7).getrandbits(64) | 1 for _ in range(9)]
+    assert both(cache, br, sets, srb, 0, scalars=sc) is True
+    bad = bytearray(sets)
+    bad[128:320] = sets[320 + 128:640]
+    assert both(cache, br, bytes(bad), srb, 0, scalars=sc) is False
+
+
+def test_api_mirror(cache, br, srb):
+    import nim_blscurve_b200 as bg
+    tp = bg.Taskpool.new(numThreads=4)
+    raw = examples(br, 6)
+    batch = [bg.SignatureSet(raw[i:i + 96], raw[i + 96:i + 128], raw[i + 128:i + 320]) for i in range(0, len(raw), 320)]
+    assert bg.batchVerify(tp, cache, batch, srb)
+    assert bg.batchVerifySerial(cache, batch, srb)
+    assert bg.batchVerifyParallel(tp, cache, batch, srb)
+    assert bg.batchVerify(tp, cache, batch[:2], srb)       # < 3 sets -> serial path
+
+
+@pytest.mark.parametrize("n,chunks", [(10, 0), (10, 4), (3, 8), (257, 16), (1000, 7)])
+def test_rlc_scalars(cache, br, srb, n, chunks):
+    import nim_blscurve_b200 as bg
+    assert bg.rlcScalars(cache, srb, n, chunks) == br.rlc_scalars(srb, n, chunks)
+
+
+def test_device_generated_sets_verify(cache, br, srb):
+    """The benchmark's synthetic generator must produce sets BLST accepts."""
+    import ctypes as C
+    import nim_blscurve_b200 as bg
+    n = 40
+    out = (C.c_uint8 * (320 * n))()
+    rc = bg.lib().blsgpu_make_sets(cache.handle, 42, 1000, n, out, 0)
+    assert rc == 0
+    sets = bytes(out)
+    assert both(cache, br, sets, srb, 4) is True
+    assert len({sets[i + 96:i + 128] for i in range(0, len(sets), 320)}) == n     # distinct messages
+    bad = bytearray(sets)
+    bad[5 * 320 + 96] ^= 1                                                        # flip one message bit
+    assert both(cache, br, bytes(bad), srb, 4) is False
