@@ -85,6 +85,15 @@ int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_device, size_t
                    const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, uint8_t partial_out[576],
                    int *flags);
 
+/* Stream-ordered forms for the multi-GPU pipeline (no host synchronisation, results stay on the device so a
+ * collective can follow on the same stream): d_partial_out = 576 bytes of device memory, d_flag_out = one
+ * device int (non-zero when a set of the share has an infinite public key). */
+int blsgpu_partial_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n, size_t first, size_t total_n,
+                       const uint8_t srb[32], uint32_t chunks, void *d_partial_out, int *d_flag_out);
+/* d_partials: count x 576 bytes on the device (e.g. the all-gather output), d_flags: count ints or NULL. */
+int blsgpu_finalize_dev(blsgpu_ctx *ctx, const void *d_partials, size_t count, const int *d_flags,
+                        uint8_t gt_out[576]);
+
 /* Product of `count` gathered partials, ONE final exponentiation, comparison with 1 (aggregate.c:494-500). */
 int blsgpu_finalize(blsgpu_ctx *ctx, const uint8_t *partials, size_t count, uint8_t gt_out[576]);
 
@@ -122,6 +131,9 @@ double blsgpu_imad_peak(blsgpu_ctx *ctx, int wide);
  * sk_i = 1 + (SHA256(seed || LE64(first+i)) mod 2^250), pk = [sk]G1, msg = SHA256("blsgpu" || LE64(first+i)),
  * sig = [sk]H(msg).  out: device pointer if out_on_device, else host. */
 int blsgpu_make_sets(blsgpu_ctx *ctx, uint64_t seed, size_t first, size_t n, void *out, int out_on_device);
+
+/* Synthetic MSM inputs on the device (benchmark only): P_i = [k_i]G1 (96-bit k_i), 255-bit coefficients. */
+int blsgpu_msm_make_inputs(blsgpu_ctx *ctx, uint64_t seed, size_t n, void *d_points96, void *d_scalars32);
 
 #ifdef __cplusplus
 }

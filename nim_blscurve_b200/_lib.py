@@ -13,9 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libblsgpu.so")
 SYMBOLS = [
     "blsgpu_device_count", "blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_capacity",
     "blsgpu_set_stream", "blsgpu_rlc_scalars", "blsgpu_batch_verify", "blsgpu_batch_verify_dev",
-    "blsgpu_partial", "blsgpu_finalize", "blsgpu_hash_to_g2", "blsgpu_aggregate_g1", "blsgpu_aggregate_g2",
+    "blsgpu_partial", "blsgpu_partial_dev", "blsgpu_finalize", "blsgpu_finalize_dev", "blsgpu_hash_to_g2", "blsgpu_aggregate_g1", "blsgpu_aggregate_g2",
     "blsgpu_msm_g1", "blsgpu_msm_g1_dev", "blsgpu_last_stage_ms", "blsgpu_stage_name", "blsgpu_last_launches",
-    "blsgpu_test_fp", "blsgpu_imad_peak", "blsgpu_make_sets",
+    "blsgpu_test_fp", "blsgpu_imad_peak", "blsgpu_make_sets", "blsgpu_msm_make_inputs",
 ]
 
 _lib = None
@@ -48,6 +48,8 @@ def lib():
     L.blsgpu_batch_verify_dev.argtypes = [vp, vp, sz, u8p, C.c_uint32, vp, vp]
     L.blsgpu_partial.argtypes = [vp, vp, C.c_int, sz, sz, sz, u8p, C.c_uint32, vp, vp, vp]
     L.blsgpu_finalize.argtypes = [vp, vp, sz, vp]
+    L.blsgpu_partial_dev.argtypes = [vp, vp, sz, sz, sz, u8p, C.c_uint32, vp, vp]
+    L.blsgpu_finalize_dev.argtypes = [vp, vp, sz, vp, vp]
     L.blsgpu_hash_to_g2.argtypes = [vp, vp, sz, sz, vp, sz, vp, vp]
     L.blsgpu_aggregate_g1.argtypes = [vp, vp, sz, vp]
     L.blsgpu_aggregate_g2.argtypes = [vp, vp, sz, vp]
@@ -61,5 +63,6 @@ def lib():
     L.blsgpu_imad_peak.restype = C.c_double
     L.blsgpu_imad_peak.argtypes = [vp, C.c_int]
     L.blsgpu_make_sets.argtypes = [vp, C.c_uint64, sz, sz, vp, C.c_int]
+    L.blsgpu_msm_make_inputs.argtypes = [vp, C.c_uint64, sz, vp, vp]
     _lib = L
     return L

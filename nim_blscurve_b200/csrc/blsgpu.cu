@@ -217,9 +217,10 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     return 0;
 }
 
-static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_inf) {
+static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_inf, const fp12 *d_partials = nullptr,
+                     const int *d_rank_flags = nullptr) {
     cudaStream_t s = ctx->stream;
-    k_final<<<1, 32, 0, s>>>(ctx->d_partials, count, ctx->d_gt, ctx->d_flags + 1);
+    k_final<<<1, 32, 0, s>>>(d_partials ? d_partials : ctx->d_partials, count, d_rank_flags, ctx->d_gt, ctx->d_flags + 1);
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[ST_COUNT], s));
     CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_gt, 576, cudaMemcpyDeviceToHost, s));
@@ -227,7 +228,7 @@ static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_in
     CK(cudaStreamSynchronize(s));
     int flags[4];
     memcpy(flags, ctx->h_pinned + 576, sizeof flags);
-    if (pk_inf) *pk_inf = flags[0];
+    if (pk_inf) *pk_inf = flags[0] | flags[2];
     if (gt_out) memcpy(gt_out, ctx->h_pinned, 576);
     return flags[1] ? 1 : 0;
 }
@@ -316,6 +317,43 @@ extern "C" int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_dev
     memcpy(f, ctx->h_pinned + 576, sizeof f);
     if (flags) *flags = f[0];
     return 0;
+}
+
+extern "C" int blsgpu_partial_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n, size_t first, size_t total_n,
+                                  const uint8_t srb[32], uint32_t chunks, void *d_partial_out, int *d_flag_out) {
+    if (!ctx || !d_partial_out) return BLSGPU_ERR_ARG;
+    if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "share larger than context capacity");
+    if (first + n > total_n) return fail(ctx, BLSGPU_ERR_ARG, "share outside the batch");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (n == 0) {
+        k_partial_one<<<1, 32, 0, s>>>((fp12 *)d_partial_out, d_flag_out);
+        CK(cudaGetLastError());
+        ctx->launches = 1;
+        return 0;
+    }
+    if (!d_sets) return fail(ctx, BLSGPU_ERR_ARG, "sets is NULL");
+    int rc = run_partial(ctx, (const sigset *)d_sets, n, first, total_n, srb, chunks, nullptr, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d_partial_out, ctx->d_partials, 576, cudaMemcpyDeviceToDevice, s));
+    if (d_flag_out) { k_copy_flag<<<1, 32, 0, s>>>(ctx->d_flags, d_flag_out); ctx->launches++; }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int blsgpu_finalize_dev(blsgpu_ctx *ctx, const void *d_partials, size_t count, const int *d_flags,
+                                   uint8_t gt_out[576]) {
+    if (!ctx || !d_partials) return BLSGPU_ERR_ARG;
+    if (gt_out) memset(gt_out, 0, 576);
+    if (count == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev[ST_FINAL], ctx->stream));
+    int bad = 0;
+    int rc = run_final(ctx, (int)count, gt_out, &bad, (const fp12 *)d_partials, d_flags);
+    collect_stage_times(ctx, true);
+    if (rc < 0) return rc;
+    if (bad) { if (gt_out) memset(gt_out, 0, 576); return 0; }
+    return rc;
 }
 
 extern "C" int blsgpu_finalize(blsgpu_ctx *ctx, const uint8_t *partials, size_t count, uint8_t gt_out[576]) {
@@ -457,6 +495,16 @@ extern "C" int blsgpu_msm_g1(blsgpu_ctx *ctx, const void *points96, const void *
     CK(cudaMemcpyAsync(base, points96, n * 96, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(base + n * 96, scalars, n * sb, cudaMemcpyHostToDevice, ctx->stream));
     return blsgpu_msm_g1_dev(ctx, base, base + n * 96, n, nbits, out96);
+}
+
+extern "C" int blsgpu_msm_make_inputs(blsgpu_ctx *ctx, uint64_t seed, size_t n, void *d_points96, void *d_scalars32) {
+    if (!ctx || !d_points96 || !d_scalars32) return BLSGPU_ERR_ARG;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    k_msm_make_inputs<<<nblk(n), 128, 0, ctx->stream>>>(seed, n, (g1_aff *)d_points96, (uint8_t *)d_scalars32);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 extern "C" int blsgpu_last_stage_ms(const blsgpu_ctx *ctx, float *ms, int max) {

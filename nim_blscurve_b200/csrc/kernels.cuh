@@ -188,6 +188,18 @@ __global__ void __launch_bounds__(128) k_miller(const g2_aff *Q, const g1_aff *P
     F[t] = f;
 }
 
+// neutral partial for an empty share: GT one in the in-memory (Montgomery) layout
+__global__ void k_partial_one(fp12 *out, int *flag_out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    fp12 one;
+    fp12_set_one(one);
+    *out = one;
+    if (flag_out) *flag_out = 0;
+}
+__global__ void k_copy_flag(const int *src, int *dst) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *dst = *src;
+}
+
 // conj(ML(S, G1)) * F  (aggregate.c:479-495); single thread
 __global__ void k_partial(const g2_jac *S, const fp12 *F, int have_sets, fp12 *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -207,8 +219,11 @@ __global__ void k_partial(const g2_jac *S, const fp12 *F, int have_sets, fp12 *o
 }
 
 // prod partials -> final exponentiation -> (== 1), canonical GT bytes
-__global__ void k_final(const fp12 *partials, int count, uint8_t *gt_bytes, int *is_one) {
+__global__ void k_final(const fp12 *partials, int count, const int *flags, uint8_t *gt_bytes, int *is_one) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int bad = 0;
+    if (flags) for (int i = 0; i < count; i++) bad |= flags[i];
+    is_one[1] = bad;
     fp12 acc = partials[0];
     for (int i = 1; i < count; i++) { fp12 b = partials[i]; fp12_mul(acc, acc, b); }
     fp12 gt;

@@ -182,6 +182,32 @@ __global__ void k_msm_horner(const g1_jac *W, size_t stride, int nwin, int c, g1
     *out = a;
 }
 
+// synthetic MSM inputs (benchmark only): P_i = [k_i]G1 with a 96-bit k_i, 255-bit coefficients
+// (shape of benchmarks/bls12381_msm_g1.nim:22-44)
+__global__ void __launch_bounds__(128) k_msm_make_inputs(uint64_t seed, size_t n, g1_aff *points, uint8_t *scalars) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = seed ^ (0xFACADEull + i * 0x100000001b3ull);
+    uint64_t v[6];
+    for (int k = 0; k < 6; k++) {
+        s += 0x9e3779b97f4a7c15ull;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        v[k] = z ^ (z >> 31);
+    }
+    uint32_t kw[3] = {(uint32_t)v[0], (uint32_t)(v[0] >> 32), (uint32_t)v[1]};
+    g1_jac g, r;
+    g.x = G1_GEN_X; g.y = G1_GEN_Y; g.z = FP_ONE;
+    pt_mul_words(r, g, kw, 3);
+    g1_aff a;
+    pt_to_affine(a, r);
+    points[i] = a;
+    for (int w = 0; w < 4; w++)
+        for (int b = 0; b < 8; b++) scalars[32 * i + 8 * w + b] = (uint8_t)(v[2 + w] >> (8 * b));
+    scalars[32 * i + 31] &= 0x7f;
+}
+
 static inline int msm_window_bits(size_t n) {
     int lg = 0;
     while ((n >> (lg + 1)) != 0) lg++;

@@ -1,0 +1,56 @@
+"""GPU parity: G1 multi-scalar multiplication vs blst_p1s_mult_pippenger (affine result, bit-exact)."""
+import ctypes as C
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 100, 1000, 4096, 20000])
+def test_msm_g1_255(cache, br, n):
+    import nim_blscurve_b200 as bg
+    pts, sc = br.msm_points(0xFACADE, n)
+    assert bg.msmG1(cache, pts, sc, 255) == br.msm_g1(pts, sc, 255)
+
+
+def test_msm_g1_edge_scalars(cache, br):
+    import nim_blscurve_b200 as bg
+    n = 64
+    pts, sc = br.msm_points(5, n)
+    sc = bytearray(sc)
+    sc[0:32] = bytes(32)                                  # zero scalar
+    sc[32:64] = b"\xff" * 31 + b"\x7f"                    # 2^255 - 1 (all digits carry)
+    sc[64:96] = b"\x01" + bytes(31)
+    sc[96:128] = bytes(31) + b"\x40"                      # single top bit
+    pts = bytearray(pts)
+    pts[96 * 5:96 * 6] = bytes(96)                        # point at infinity
+    pts[96 * 7:96 * 8] = pts[96 * 6:96 * 7]               # repeated point (bucket doubling)
+    sc[32 * 7:32 * 8] = sc[32 * 6:32 * 7]
+    assert bg.msmG1(cache, bytes(pts), bytes(sc), 255) == br.msm_g1(bytes(pts), bytes(sc), 255)
+
+
+@pytest.mark.parametrize("nbits", [64, 128, 200])
+def test_msm_g1_short_scalars(cache, br, nbits):
+    """nbits=64 is the shape MultiSignatureSet.combine uses (blst_min_pubkey_sig_core.nim:629-636)."""
+    import nim_blscurve_b200 as bg
+    n = 257
+    pts, _ = br.msm_points(9, n)
+    rng = random.Random(nbits)
+    sb = (nbits + 7) // 8
+    sc = b"".join(rng.getrandbits(nbits).to_bytes(sb, "little") for _ in range(n))
+    assert bg.msmG1(cache, pts, sc, nbits) == br.msm_g1(pts, sc, nbits)
+
+
+def test_msm_device_inputs_match_oracle(cache, br):
+    """The benchmark's device-side input generator + MSM against BLST on the same bytes."""
+    import torch
+    import nim_blscurve_b200 as bg
+    n = 3000
+    dp = torch.empty(n * 96, dtype=torch.uint8, device="cuda")
+    ds = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    L = bg.lib()
+    assert L.blsgpu_msm_make_inputs(cache.handle, 11, n, C.c_void_p(dp.data_ptr()), C.c_void_p(ds.data_ptr())) == 0
+    out = (C.c_uint8 * 96)()
+    assert L.blsgpu_msm_g1_dev(cache.handle, C.c_void_p(dp.data_ptr()), C.c_void_p(ds.data_ptr()), n, 255, out) == 1
+    assert bytes(out) == br.msm_g1(dp.cpu().numpy().tobytes(), ds.cpu().numpy().tobytes(), 255)
