@@ -127,6 +127,8 @@ int blsgpu_last_launches(const blsgpu_ctx *ctx);
 int blsgpu_test_fp(blsgpu_ctx *ctx, int op, const void *a, const void *b, size_t n, void *out);
 /* Integer-multiply pipe microbenchmark: returns measured 32x32->64 multiply-accumulates per second. */
 double blsgpu_imad_peak(blsgpu_ctx *ctx, int wide);
+/* Register-resident Montgomery multiplications per second of this library's fp_mul (no memory traffic). */
+double blsgpu_fpmul_peak(blsgpu_ctx *ctx, int threads_per_block, int blocks_per_sm);
 /* Generate n valid signature sets on the device (synthetic workload for benchmarks):
  * sk_i = 1 + (SHA256(seed || LE64(first+i)) mod 2^250), pk = [sk]G1, msg = SHA256("blsgpu" || LE64(first+i)),
  * sig = [sk]H(msg).  out: device pointer if out_on_device, else host. */

@@ -12,3 +12,4 @@ from .batch_verifier import (  # noqa: F401
     BatchedBLSVerifierCache, SignatureSet, Taskpool, aggregateAll, batchVerify, batchVerifyParallel,
     batchVerifySerial, hashToG2, msmG1, rlcScalars,
 )
+from .multi_gpu import GpuBackend, batch_verify_distributed, shard_range  # noqa: F401,E402

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblsgpu.so")
+LIB_PATH = os.environ.get("BLSGPU_LIB") or os.path.join(_HERE, "libblsgpu.so")   # env override: kernel-variant experiments
 
 # every symbol include/blsgpu.h declares (tests check the export list against the header)
 SYMBOLS = [
@@ -15,7 +15,7 @@ SYMBOLS = [
     "blsgpu_set_stream", "blsgpu_rlc_scalars", "blsgpu_batch_verify", "blsgpu_batch_verify_dev",
     "blsgpu_partial", "blsgpu_partial_dev", "blsgpu_finalize", "blsgpu_finalize_dev", "blsgpu_hash_to_g2", "blsgpu_aggregate_g1", "blsgpu_aggregate_g2",
     "blsgpu_msm_g1", "blsgpu_msm_g1_dev", "blsgpu_last_stage_ms", "blsgpu_stage_name", "blsgpu_last_launches",
-    "blsgpu_test_fp", "blsgpu_imad_peak", "blsgpu_make_sets", "blsgpu_msm_make_inputs",
+    "blsgpu_test_fp", "blsgpu_imad_peak", "blsgpu_fpmul_peak", "blsgpu_make_sets", "blsgpu_msm_make_inputs",
 ]
 
 _lib = None
@@ -62,6 +62,8 @@ def lib():
     L.blsgpu_test_fp.argtypes = [vp, C.c_int, vp, vp, sz, vp]
     L.blsgpu_imad_peak.restype = C.c_double
     L.blsgpu_imad_peak.argtypes = [vp, C.c_int]
+    L.blsgpu_fpmul_peak.restype = C.c_double
+    L.blsgpu_fpmul_peak.argtypes = [vp, C.c_int, C.c_int]
     L.blsgpu_make_sets.argtypes = [vp, C.c_uint64, sz, sz, vp, C.c_int]
     L.blsgpu_msm_make_inputs.argtypes = [vp, C.c_uint64, sz, vp, vp]
     _lib = L

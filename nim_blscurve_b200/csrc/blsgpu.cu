@@ -393,39 +393,6 @@ extern "C" int blsgpu_hash_to_g2(blsgpu_ctx *ctx, const uint8_t *msgs, size_t n,
     return 0;
 }
 
-extern "C" int blsgpu_debug_h2c(blsgpu_ctx *ctx, const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, void *out) {
-    if (!ctx) return BLSGPU_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    int rc = ensure_misc(ctx, 4096 + sizeof(h2c_trace) + msg_len);
-    if (rc) return rc;
-    uint8_t *base = (uint8_t *)ctx->d_misc;
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(base, dst, dst_len, cudaMemcpyHostToDevice, s));
-    if (msg_len) CK(cudaMemcpyAsync(base + 256, msg, msg_len, cudaMemcpyHostToDevice, s));
-    h2c_trace *t = (h2c_trace *)(base + 256 + ((msg_len + 255) & ~(size_t)255));
-    k_h2c_trace<<<1, 32, 0, s>>>(base + 256, msg_len, base, (uint32_t)dst_len, t);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, t, sizeof(h2c_trace), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return (int)sizeof(h2c_trace);
-}
-
-extern "C" int blsgpu_debug2(blsgpu_ctx *ctx, const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, void *out) {
-    CK(cudaSetDevice(ctx->device));
-    int rc = ensure_misc(ctx, 8192 + msg_len);
-    if (rc) return rc;
-    uint8_t *base = (uint8_t *)ctx->d_misc;
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(base, dst, dst_len, cudaMemcpyHostToDevice, s));
-    if (msg_len) CK(cudaMemcpyAsync(base + 256, msg, msg_len, cudaMemcpyHostToDevice, s));
-    uint8_t *o = base + 256 + ((msg_len + 255) & ~(size_t)255);
-    k_dbg2<<<1, 128, 0, s>>>(base + 256, 1, msg_len, base, (uint32_t)dst_len, (g2_jac *)o, (g2_aff *)(o + 288));
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, o, 480, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return 480;
-}
-
 extern "C" int blsgpu_aggregate_g1(blsgpu_ctx *ctx, const void *points96, size_t n, uint8_t out96[96]) {
     if (!ctx || !out96) return BLSGPU_ERR_ARG;
     if (n == 0) return 0;                                   // blst_min_pubkey_sig_core.nim:183-184
@@ -555,6 +522,33 @@ extern "C" double blsgpu_imad_peak(blsgpu_ctx *ctx, int wide) {
         cudaEventElapsedTime(&ms, e0, e1);
         double ops = (double)blocks * threads * iters * 64.0;
         double rate = ops / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+}
+
+extern "C" double blsgpu_fpmul_peak(blsgpu_ctx *ctx, int threads_per_block, int blocks_per_sm) {
+    if (!ctx) return -1.0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
+    if (ensure_misc(ctx, 256)) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return -1.0;
+    const int iters = 2000, blocks = prop.multiProcessorCount * blocks_per_sm;
+    cudaStream_t s = ctx->stream;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, s);
+        k_fpmul_peak<<<blocks, threads_per_block, 0, s>>>((fp *)ctx->d_misc, iters, 99u + rep);
+        cudaEventRecord(e1, s);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double rate = (double)blocks * threads_per_block * iters * 2.0 / (ms * 1e-3);
         if (rep > 0 && rate > best) best = rate;
     }
     cudaEventDestroy(e0);

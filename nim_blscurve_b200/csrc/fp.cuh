@@ -263,6 +263,10 @@ BLS_FN void fp_mul(fp &r, const fp &a, const fp &b) {
     add12(O, E + 1);
     reduce_once12(r.l, O);
 #else
+#ifdef BLS_COUNT_MULS
+    extern unsigned long long g_fp_mul_count;
+    g_fp_mul_count++;
+#endif
     uint32_t t[14];
     for (int i = 0; i < 14; i++) t[i] = 0;
     for (int i = 0; i < 12; i++) {

@@ -17,6 +17,12 @@
 
 namespace bls {
 
+// heavy kernels: at most 128 registers -> 4 blocks of 128 threads (16 warps) per SM
+#ifndef BLS_LB_BLOCKS
+#define BLS_LB_BLOCKS 2
+#endif
+#define BLS_LB __launch_bounds__(128, BLS_LB_BLOCKS)
+
 struct sigset { g1_aff pk; uint8_t msg[32]; g2_aff sig; };
 static_assert(sizeof(sigset) == 320, "SignatureSet layout (bls_batch_verifier.nim:34)");
 static_assert(sizeof(fp12) == 576 && sizeof(g2_jac) == 288 && sizeof(g1_jac) == 144, "layout");
@@ -88,7 +94,7 @@ __global__ void k_rlc_scalars(words8 srb, size_t total_n, uint32_t chunks, size_
     }
 }
 
-__global__ void __launch_bounds__(128) k_hash_sets(const sigset *sets, size_t n, g2_jac *H) {
+__global__ void BLS_LB k_hash_sets(const sigset *sets, size_t n, g2_jac *H) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t msg[32], dst[43];
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(128) k_hash_sets(const sigset *sets, size_t n,
     H[i] = h;
 }
 
-__global__ void __launch_bounds__(128) k_g1_mul(const sigset *sets, const uint64_t *r, size_t n, g1_jac *Pj, int *flags) {
+__global__ void BLS_LB k_g1_mul(const sigset *sets, const uint64_t *r, size_t n, g1_jac *Pj, int *flags) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1_aff pk = sets[i].pk;
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(128) k_g1_mul(const sigset *sets, const uint64
 }
 
 // H_i and [r_i]pk_i to affine with ONE Fermat inversion per set (Montgomery's trick on N(Z_H) and Z_P)
-__global__ void __launch_bounds__(128) k_pairs_affine(const g2_jac *H, const g1_jac *Pj, size_t n, g2_aff *Q, g1_aff *P) {
+__global__ void BLS_LB k_pairs_affine(const g2_jac *H, const g1_jac *Pj, size_t n, g2_aff *Q, g1_aff *P) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_jac h = H[i];
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(128) k_pairs_affine(const g2_jac *H, const g1_
     P[i] = a;
 }
 
-__global__ void __launch_bounds__(128) k_g2_mul(const sigset *sets, const uint64_t *r, size_t n, g2_jac *S) {
+__global__ void BLS_LB k_g2_mul(const sigset *sets, const uint64_t *r, size_t n, g2_jac *S) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_aff sig = sets[i].sig;
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(128) k_g2_mul(const sigset *sets, const uint64
 }
 
 // pairwise tree step: x[i] (op)= x[i + half] for i + half < n
-__global__ void __launch_bounds__(128) k_g2_tree(g2_jac *S, size_t n, size_t half) {
+__global__ void BLS_LB k_g2_tree(g2_jac *S, size_t n, size_t half) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half || i + half >= n) return;
     g2_jac a = S[i], b = S[i + half];
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(128) k_g2_tree(g2_jac *S, size_t n, size_t hal
     S[i] = a;
 }
 
-__global__ void __launch_bounds__(128) k_g1_tree(g1_jac *S, size_t n, size_t half) {
+__global__ void BLS_LB k_g1_tree(g1_jac *S, size_t n, size_t half) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half || i + half >= n) return;
     g1_jac a = S[i], b = S[i + half];
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(128) k_g1_tree(g1_jac *S, size_t n, size_t hal
     S[i] = a;
 }
 
-__global__ void __launch_bounds__(128) k_fp12_tree(fp12 *F, size_t n, size_t half) {
+__global__ void BLS_LB k_fp12_tree(fp12 *F, size_t n, size_t half) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half || i + half >= n) return;
     fp12 a = F[i], b = F[i + half];
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(128) k_fp12_tree(fp12 *F, size_t n, size_t hal
 }
 
 template <int G>
-__global__ void __launch_bounds__(128) k_miller(const g2_aff *Q, const g1_aff *P, size_t n, fp12 *F) {
+__global__ void __launch_bounds__(64, 2 * BLS_LB_BLOCKS) k_miller(const g2_aff *Q, const g1_aff *P, size_t n, fp12 *F) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t base = t * G;
     if (base >= n) return;
@@ -233,7 +239,7 @@ __global__ void k_final(const fp12 *partials, int count, const int *flags, uint8
 }
 
 // ---- generic hash_to_G2 entry (arbitrary message length and DST, both in global memory) ----
-__global__ void __launch_bounds__(128) k_hash_to_g2(const uint8_t *msgs, size_t n, size_t msg_len, const uint8_t *dst,
+__global__ void BLS_LB k_hash_to_g2(const uint8_t *msgs, size_t n, size_t msg_len, const uint8_t *dst,
                                                     uint32_t dst_len, g2_aff *out_aff, uint8_t *out_comp) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -245,37 +251,6 @@ __global__ void __launch_bounds__(128) k_hash_to_g2(const uint8_t *msgs, size_t 
     if (out_comp) g2_compress(out_comp + 96 * i, a);
 }
 
-// stage-by-stage dump of hash_to_G2 for debugging: u0,u1 | q0 | q1 | q0+q1 | iso | cleared (Jacobian) | affine
-struct h2c_trace { fp2 u0, u1; g2_jac q0, q1, sum, iso, out; g2_aff aff; g2_jac alt; g2_aff alt_aff; };
-__device__ __forceinline__ void h2c_trace_run(h2c_trace &t, const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len) {
-    hash_to_field_fp2x2(t.u0, t.u1, msg, msg_len, dst, dst_len);
-    sswu_g2(t.q0, t.u0);
-    sswu_g2(t.q1, t.u1);
-    pt_add(t.sum, t.q0, t.q1, &SSWU_A);
-    iso3_g2(t.iso, t.sum);
-    g2_clear_cofactor(t.out, t.iso);
-    pt_to_affine(t.aff, t.out);
-    hash_to_g2_jac(t.alt, msg, msg_len, dst, dst_len);
-    pt_to_affine(t.alt_aff, t.alt);
-}
-__global__ void k_h2c_trace(const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len, h2c_trace *out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    h2c_trace t;
-    h2c_trace_run(t, msg, msg_len, dst, dst_len);
-    *out = t;
-}
-
-__global__ void __launch_bounds__(128) k_dbg2(const uint8_t *msgs, size_t n, size_t msg_len, const uint8_t *dst,
-                                              uint32_t dst_len, g2_jac *out_jac, g2_aff *out_aff) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    g2_jac h;
-    hash_to_g2_jac(h, msgs + i * msg_len, msg_len, dst, dst_len);
-    out_jac[i] = h;
-    g2_aff a;
-    pt_to_affine(a, h);
-    out_aff[i] = a;
-}
 // ---- aggregateAll helpers ----
 __global__ void __launch_bounds__(128) k_g1_load(const g1_aff *in, size_t n, g1_jac *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,8 +334,23 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters, ui
     }
 }
 
+// Register-resident Fp multiplication throughput (ceiling of this fp_mul implementation): every thread runs a
+// dependent chain x <- x*y, y <- y*x with no memory traffic.
+__global__ void k_fpmul_peak(fp *sink, int iters, uint32_t seed) {
+    fp x, y;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { x.l[i] = seed + i + threadIdx.x; y.l[i] = seed * 7 + i + blockIdx.x; }
+    x.l[11] &= 0x0fffffffu;
+    y.l[11] &= 0x0fffffffu;
+    for (int i = 0; i < iters; i++) {
+        fp_mul(x, x, y);
+        fp_mul(y, y, x);
+    }
+    if (x.l[0] == 0x12345 && y.l[3] == 0x54321) sink[0] = x;
+}
+
 // Synthetic valid signature sets, generated on the device (benchmark input only).
-__global__ void __launch_bounds__(128) k_make_sets(words8 seed, size_t first, size_t n, sigset *out) {
+__global__ void BLS_LB k_make_sets(words8 seed, size_t first, size_t n, sigset *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t idx = first + i;

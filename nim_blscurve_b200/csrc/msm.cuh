@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *scalars, siz
     }
 }
 
-__global__ void __launch_bounds__(128) k_msm_bucket(const g1_aff *points, const uint32_t *offsets, const uint32_t *entries,
+__global__ void BLS_LB k_msm_bucket(const g1_aff *points, const uint32_t *offsets, const uint32_t *entries,
                                                     size_t nbuckets, g1_jac *buckets) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nbuckets) return;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) k_msm_bucket(const g1_aff *points, const 
 
 // segment j of window w covers digit magnitudes b in [j*SEG+1, j*SEG+SEG] (bucket index b-1):
 //   T = sum_b (b - j*SEG) B_b  +  [j*SEG] sum_b B_b
-__global__ void __launch_bounds__(128) k_msm_segment(const g1_jac *buckets, int c, int nwin, g1_jac *segs) {
+__global__ void BLS_LB k_msm_segment(const g1_jac *buckets, int c, int nwin, g1_jac *segs) {
     const uint32_t B = 1u << (c - 1);
     const uint32_t L = B < MSM_SEG ? B : MSM_SEG;
     const uint32_t nseg = B / L;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) k_msm_segment(const g1_jac *buckets, int 
 }
 
 // row-wise pairwise tree step over `rows` rows of `stride` entries
-__global__ void __launch_bounds__(128) k_g1_tree_rows(g1_jac *S, int rows, size_t stride, size_t m, size_t half) {
+__global__ void BLS_LB k_g1_tree_rows(g1_jac *S, int rows, size_t stride, size_t m, size_t half) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)rows * half) return;
     size_t r = t / half, i = t % half;
@@ -184,7 +184,7 @@ __global__ void k_msm_horner(const g1_jac *W, size_t stride, int nwin, int c, g1
 
 // synthetic MSM inputs (benchmark only): P_i = [k_i]G1 with a 96-bit k_i, 255-bit coefficients
 // (shape of benchmarks/bls12381_msm_g1.nim:22-44)
-__global__ void __launch_bounds__(128) k_msm_make_inputs(uint64_t seed, size_t n, g1_aff *points, uint8_t *scalars) {
+__global__ void BLS_LB k_msm_make_inputs(uint64_t seed, size_t n, g1_aff *points, uint8_t *scalars) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t s = seed ^ (0xFACADEull + i * 0x100000001b3ull);

@@ -1,0 +1,71 @@
+# blscurve/cuda/bls_batch_verifier_cuda.nim — drop-in bodies for blscurve/bls_batch_verifier.nim.
+#
+# Public names, parameter lists and results are those of the reference (file:line into nim-blscurve):
+#   SignatureSet :34, BatchedBLSVerifierCache :62, init :108/:115, batchVerifySerial :121/:162,
+#   batchVerifyParallel :296/:373/:399, batchVerify :420/:449/:475, aggregateAll (blst_min_pubkey_sig_core.nim:179).
+# `tp: Taskpool` stays in the signatures; it no longer fans work out — tp.numThreads only selects the reference's
+# RLC-scalar chunking, so verdicts (and GT values) are identical to the BLST path for the same tp.
+# NOT compiled in the build container (no Nim toolchain); see INTEGRATION.md.
+{.push raises: [].}
+
+import taskpools
+import ../blst/blst_min_pubkey_sig_core   # PublicKey, Signature (in-memory blst_p1_affine / blst_p2_affine)
+import ./blsgpu_abi
+
+type
+  SignatureSet* = tuple[pubkey: PublicKey, message: array[32, byte], signature: Signature]
+
+  BatchedBLSVerifierCache* {.requiresInit.} = object
+    ## device scratch instead of per-thread pairing contexts
+    ctx: BlsGpuCtx
+    numThreads: int
+
+static: doAssert sizeof(SignatureSet) == 320   # pk 96 | msg 32 | sig 192, no padding
+
+proc `=destroy`(c: var BatchedBLSVerifierCache) =
+  if not pointer(c.ctx).isNil: blsgpu_destroy(c.ctx)
+
+func init*(T: type BatchedBLSVerifierCache, maxSets = 16384, device = 0): T =
+  T(ctx: blsgpu_create(device.cint, maxSets.csize_t), numThreads: 1)
+
+func init*(T: type BatchedBLSVerifierCache, tp: Taskpool, maxSets = 16384, device = 0): T =
+  T(ctx: blsgpu_create(device.cint, maxSets.csize_t), numThreads: tp.numThreads)
+
+func verifyRaw(cache: var BatchedBLSVerifierCache, sets: ptr UncheckedArray[SignatureSet], n: int,
+               srb: ptr array[32, byte], chunks: uint32): bool =
+  if n == 0: return false                                    # spec precondition (:137, :312)
+  doAssert not pointer(cache.ctx).isNil, "blsgpu_create failed: no CUDA device (there is no CPU fallback)"
+  # 1 valid / 0 invalid / <0 CUDA failure -> false (+ blsgpu_last_error for diagnostics)
+  blsgpu_batch_verify(cache.ctx, sets, n.csize_t, srb, chunks, nil, nil) == 1
+
+func batchVerifySerial*(cache: var BatchedBLSVerifierCache, input: openArray[SignatureSet],
+                        secureRandomBytes: array[32, byte]): bool =
+  if input.len == 0: return false
+  cache.verifyRaw(cast[ptr UncheckedArray[SignatureSet]](unsafeAddr input[0]), input.len,
+                  unsafeAddr secureRandomBytes, 0'u32)
+
+proc batchVerifyParallel*(tp: Taskpool, cache: var BatchedBLSVerifierCache, input: openArray[SignatureSet],
+                          secureRandomBytes: array[32, byte]): bool =
+  if input.len == 0: return false
+  cache.verifyRaw(cast[ptr UncheckedArray[SignatureSet]](unsafeAddr input[0]), input.len,
+                  unsafeAddr secureRandomBytes, uint32 max(1, tp.numThreads))
+
+proc batchVerify*(tp: Taskpool, cache: var BatchedBLSVerifierCache, input: openArray[SignatureSet],
+                  secureRandomBytes: array[32, byte]): bool =
+  if tp.numThreads > 1 and input.len >= 3:                   # same rule as :440, :468
+    tp.batchVerifyParallel(cache, input, secureRandomBytes)
+  else:
+    cache.batchVerifySerial(input, secureRandomBytes)
+
+proc batchVerify*(tp: Taskpool, input: openArray[SignatureSet], secureRandomBytes: array[32, byte]): bool =
+  var cache = BatchedBLSVerifierCache.init(tp, maxSets = max(1, input.len))
+  tp.batchVerify(cache, input, secureRandomBytes)
+
+func aggregateAll*(cache: var BatchedBLSVerifierCache, dst: var PublicKey, elems: openArray[PublicKey]): bool =
+  if elems.len == 0: return false                            # blst_min_pubkey_sig_core.nim:183-184
+  blsgpu_aggregate_g1(cache.ctx, unsafeAddr elems[0], elems.len.csize_t, addr dst) == 1
+
+func aggregateAll*(cache: var BatchedBLSVerifierCache, dst: var Signature, elems: openArray[Signature]): bool =
+  if elems.len == 0: return false
+  blsgpu_aggregate_g2(cache.ctx, unsafeAddr elems[0], elems.len.csize_t, addr dst) == 1
+{.pop.}

@@ -1,0 +1,40 @@
+# blscurve/cuda/blsgpu_abi.nim — FFI declarations of libblsgpu.so (include/blsgpu.h).
+#
+# Same idioms as blscurve/blst/blst_abi.nim (importc, cdecl, raw pointers, `bool`-like cint results):
+# NOT compiled in the build container (no Nim toolchain there); kept in-tree as the reference-side binding
+# a maintainer adds.  See INTEGRATION.md.
+{.push raises: [].}
+
+const blsgpuLib* {.strdefine.} = "libblsgpu.so"
+
+type
+  BlsGpuCtx* = distinct pointer
+
+{.push cdecl, dynlib: blsgpuLib, importc.}
+proc blsgpu_device_count*(): cint
+proc blsgpu_create*(device: cint, maxSets: csize_t): BlsGpuCtx
+proc blsgpu_destroy*(ctx: BlsGpuCtx)
+proc blsgpu_last_error*(ctx: BlsGpuCtx): cstring
+proc blsgpu_capacity*(ctx: BlsGpuCtx): csize_t
+proc blsgpu_set_stream*(ctx: BlsGpuCtx, cudaStream: pointer): cint
+proc blsgpu_rlc_scalars*(ctx: BlsGpuCtx, srb: ptr array[32, byte], n: csize_t, chunks: uint32,
+                         dst: ptr uint64): cint
+proc blsgpu_batch_verify*(ctx: BlsGpuCtx, sets: pointer, n: csize_t, srb: ptr array[32, byte],
+                          chunks: uint32, scalars: ptr uint64, gtOut: ptr array[576, byte]): cint
+proc blsgpu_batch_verify_dev*(ctx: BlsGpuCtx, dSets: pointer, n: csize_t, srb: ptr array[32, byte],
+                              chunks: uint32, scalars: ptr uint64, gtOut: ptr array[576, byte]): cint
+proc blsgpu_partial*(ctx: BlsGpuCtx, sets: pointer, setsOnDevice: cint, n, first, totalN: csize_t,
+                     srb: ptr array[32, byte], chunks: uint32, scalars: ptr uint64,
+                     partialOut: ptr array[576, byte], flags: ptr cint): cint
+proc blsgpu_partial_dev*(ctx: BlsGpuCtx, dSets: pointer, n, first, totalN: csize_t, srb: ptr array[32, byte],
+                         chunks: uint32, dPartialOut: pointer, dFlagOut: ptr cint): cint
+proc blsgpu_finalize*(ctx: BlsGpuCtx, partials: ptr byte, count: csize_t, gtOut: ptr array[576, byte]): cint
+proc blsgpu_finalize_dev*(ctx: BlsGpuCtx, dPartials: pointer, count: csize_t, dFlags: ptr cint,
+                          gtOut: ptr array[576, byte]): cint
+proc blsgpu_hash_to_g2*(ctx: BlsGpuCtx, msgs: ptr byte, n, msgLen: csize_t, dst: ptr byte, dstLen: csize_t,
+                        outCompressed, outAffine: ptr byte): cint
+proc blsgpu_aggregate_g1*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: pointer): cint
+proc blsgpu_aggregate_g2*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: pointer): cint
+proc blsgpu_msm_g1*(ctx: BlsGpuCtx, points, scalars: pointer, n, nbits: csize_t, dst: pointer): cint
+{.pop.}
+{.pop.}

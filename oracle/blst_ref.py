@@ -44,6 +44,8 @@ ref.ref_fast_aggregate_set.restype = C.c_int
 ref.ref_time_batch_verify.restype = C.c_double
 ref.ref_time_msm_g1.restype = C.c_double
 ref.ref_ncores.restype = C.c_int
+ref.ref_partial.restype = C.c_int
+ref.ref_finalize.restype = C.c_int
 
 
 def make_sets(start_seed, n, msg_prefix=b"msg", threads=0):
@@ -187,3 +189,19 @@ def fp_op(op, a48, b48=None):
 
 def ncores():
     return int(ref.ref_ncores())
+
+
+def partial(sets, first, total_n, srb, chunks):
+    """One rank's 576-byte Fp12 partial (BLST in-memory layout) and its failure flag."""
+    n = len(sets) // 320
+    out, flag = _out(576), C.c_int(0)
+    ref.ref_partial(_buf(sets) if n else None, C.c_size_t(n), C.c_size_t(first), C.c_size_t(total_n), _buf(srb),
+                    C.c_uint32(chunks), out, C.byref(flag))
+    return bytes(out), int(flag.value)
+
+
+def finalize(partials):
+    count = len(partials) // 576
+    gt = _out(576)
+    ok = ref.ref_finalize(_buf(partials), C.c_size_t(count), gt)
+    return bool(ok), bytes(gt)

@@ -412,3 +412,42 @@ void ref_combine(const uint8_t srb[32], const uint8_t *pks, const uint8_t *sigs,
     blst_p2_to_affine((blst_p2_affine *)sig_out, &r2);
     free(scratch); free(sc);
 }
+
+/* ---------------- multi-rank decomposition ----------------
+ * One rank's share [first, first+n) of a batch of total_n sets: scalars come from the GLOBAL derivation, the
+ * partial is conj(ML(S_k, G1)) * prod ML([r_i]pk_i, H(m_i)) in BLST's in-memory fp12 layout.  By bilinearity the
+ * product of all partials, finally exponentiated, equals the single-context result of ref_batch_verify. */
+int ref_partial(const uint8_t *sets_, size_t n, size_t first, size_t total_n, const uint8_t srb[32], uint32_t chunks,
+                uint8_t partial_out[576], int *flag) {
+    const sigset_t320 *sets = (const sigset_t320 *)sets_;
+    blst_fp12 acc = *blst_fp12_one();
+    *flag = 0;
+    if (n) {
+        uint64_t *r = malloc(8 * total_n);
+        ref_rlc_scalars(srb, total_n, chunks, r);
+        blst_pairing *ctx = malloc(blst_pairing_sizeof());
+        if (!run_chunk(ctx, sets, 0, n, srb, 0, 0, r + first)) { *flag = 1; }
+        else {
+            blst_p2 S; int any; blst_fp12 gs;
+            sum_rsig(&S, &any, sets, n, r + first);
+            if (any) { blst_p2_affine Sa; blst_p2_to_affine(&Sa, &S); blst_miller_loop(&gs, &Sa, blst_p1_affine_generator()); }
+            else gs = *blst_fp12_one();
+            blst_fp12_conjugate(&gs);
+            blst_fp12_mul(&acc, &gs, blst_pairing_as_fp12(ctx));
+        }
+        free(ctx); free(r);
+    }
+    memcpy(partial_out, &acc, 576);
+    return 1;
+}
+
+int ref_finalize(const uint8_t *partials, size_t count, uint8_t gt_out[576]) {
+    memset(gt_out, 0, 576);
+    if (count == 0) return 0;
+    blst_fp12 acc, t;
+    memcpy(&acc, partials, 576);
+    for (size_t i = 1; i < count; i++) { memcpy(&t, partials + 576 * i, 576); blst_fp12_mul(&acc, &acc, &t); }
+    blst_final_exp(&acc, &acc);
+    blst_bendian_from_fp12(gt_out, &acc);
+    return blst_fp12_is_one(&acc) ? 1 : 0;
+}

@@ -38,17 +38,52 @@ void hs_miller_loop_n(const g2_aff *Q, const g1_aff *P, int n, fp12 *f) {
 }
 void hs_final_exp(const fp12 *f, fp12 *r) { final_exp(*r, *f); }
 
-struct h2c_trace { fp2 u0, u1; g2_jac q0, q1, sum, iso, out; g2_aff aff; g2_jac alt; g2_aff alt_aff; };
-int hs_h2c_trace(const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len, h2c_trace *t) {
-    hash_to_field_fp2x2(t->u0, t->u1, msg, msg_len, dst, dst_len);
-    sswu_g2(t->q0, t->u0);
-    sswu_g2(t->q1, t->u1);
-    pt_add(t->sum, t->q0, t->q1, &SSWU_A);
-    iso3_g2(t->iso, t->sum);
-    g2_clear_cofactor(t->out, t->iso);
-    pt_to_affine(t->aff, t->out);
-    hash_to_g2_jac(t->alt, msg, msg_len, dst, dst_len);
-    pt_to_affine(t->alt_aff, t->alt);
-    return (int)sizeof(h2c_trace);
+// whole batch-verification pipeline as the kernels of kernels.cuh sequence it, executed on the host
+struct hs_sigset { g1_aff pk; uint8_t msg[32]; g2_aff sig; };
+int hs_batch_verify(const hs_sigset *sets, size_t n, const uint64_t *r, int group, uint8_t *gt_out) {
+    static const uint8_t dst[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_";
+    memset(gt_out, 0, 576);
+    if (n == 0) return 0;
+    g2_aff *Q = new g2_aff[n];
+    g1_aff *P = new g1_aff[n];
+    g2_jac S; pt_set_inf(S);
+    int pk_inf = 0;
+    for (size_t i = 0; i < n; i++) {
+        g2_jac h; hash_to_g2_jac(h, sets[i].msg, 32, dst, 43);
+        if (aff_is_inf(sets[i].pk)) pk_inf = 1;
+        g1_jac pj; pt_mul_u64(pj, sets[i].pk, r[i]);
+        pt_to_affine(Q[i], h);
+        pt_to_affine(P[i], pj);
+        g2_jac sj; pt_mul_u64(sj, sets[i].sig, r[i]);
+        pt_add(S, S, sj);
+    }
+    fp12 F; fp12_set_one(F);
+    for (size_t base = 0; base < n; base += group) {
+        int cnt = (int)((n - base) < (size_t)group ? (n - base) : (size_t)group);
+        g2_jac T[8]; fp npx[8]; fp12 f;
+        miller_loop_n(f, Q + base, P + base, cnt, T, npx);
+        fp12_mul(F, F, f);
+    }
+    g2_aff sa; pt_to_affine(sa, S);
+    g1_aff g; g.x = G1_GEN_X; g.y = G1_GEN_Y;
+    fp12 gs; g2_jac T[1]; fp npx[1];
+    miller_loop_n(gs, &sa, &g, 1, T, npx);
+    fp12_conj(gs, gs);
+    fp12_mul(gs, gs, F);
+    fp12 gt; final_exp(gt, gs);
+    fp12_to_bytes(gt_out, gt);
+    delete[] Q; delete[] P;
+    if (pk_inf) { memset(gt_out, 0, 576); return 0; }
+    return fp12_is_one(gt) ? 1 : 0;
+}
+void hs_aggregate_g1(const g1_aff *p, size_t n, g1_aff *out) {
+    g1_jac acc; pt_from_affine(acc, p[0]);
+    for (size_t i = 1; i < n; i++) { g1_jac t; pt_from_affine(t, p[i]); pt_add(acc, acc, t); }
+    pt_to_affine(*out, acc);
+}
+void hs_aggregate_g2(const g2_aff *p, size_t n, g2_aff *out) {
+    g2_jac acc; pt_from_affine(acc, p[0]);
+    for (size_t i = 1; i < n; i++) { g2_jac t; pt_from_affine(t, p[i]); pt_add(acc, acc, t); }
+    pt_to_affine(*out, acc);
 }
 }
