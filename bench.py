@@ -159,9 +159,9 @@ def main():
             rc = L.blsgpu_finalize_dev(h, C.c_void_p(d_partial.data_ptr()), 1, C.c_void_p(d_flag.data_ptr()), gt)
         launches[0] += 1
         assert rc == 1, f"synthetic batch must verify (rc={rc}) {cache.last_error()}"
-        ms = (C.c_float * 10)()
-        L.blsgpu_last_stage_ms(h, ms, 10)
-        for i in range(10):
+        ms = (C.c_float * 16)()
+        k = L.blsgpu_last_stage_ms(h, ms, 16)
+        for i in range(k):
             nm = L.blsgpu_stage_name(i).decode()
             stage_acc[nm] = stage_acc.get(nm, 0.0) + ms[i]
 

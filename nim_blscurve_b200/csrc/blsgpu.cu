@@ -13,9 +13,11 @@
 
 using namespace bls;
 
-enum { ST_SCALARS = 0, ST_HASH, ST_G1MUL, ST_AFFINE, ST_G2MUL, ST_G2SUM, ST_MILLER, ST_GTPROD, ST_PARTIAL, ST_FINAL, ST_COUNT };
-static const char *STAGE_NAMES[ST_COUNT] = {"rlc_scalars", "hash_to_g2", "g1_mul64", "pairs_affine", "g2_mul64",
-                                            "g2_sum", "miller_loop", "gt_product", "partial", "final_exp"};
+enum { ST_SCALARS = 0, ST_G2MUL, ST_G2SUM, ST_HASH, ST_G1MUL, ST_AFFINE, ST_LINES, ST_ACC, ST_GTPROD, ST_PARTIAL, ST_FINAL, ST_COUNT };
+static const char *STAGE_NAMES[ST_COUNT] = {"rlc_scalars", "g2_mul64", "g2_sum", "hash_to_g2", "g1_mul64", "pairs_affine",
+                                            "miller_lines", "miller_acc", "gt_product", "partial", "final_exp"};
+// Miller-loop tiling: at most LINES_TILE pairs have their 68 x 288-byte line triples resident at once
+static const size_t LINES_TILE = (size_t)1 << 18;
 
 struct blsgpu_ctx {
     int device = 0;
@@ -29,7 +31,11 @@ struct blsgpu_ctx {
     g2_aff *d_Q = nullptr;
     g1_aff *d_P = nullptr;
     g2_jac *d_S = nullptr;
-    fp12 *d_F = nullptr;
+    fp12 *d_F = nullptr;          // per-segment block products, nseg rows
+    size_t f_cap = 0;
+    fp12 *d_seg = nullptr;        // 64 segment products
+    uint32_t *d_lines = nullptr;  // 68 x 72 words x lines_stride
+    size_t lines_cap = 0;         // pairs per tile
     fp12 *d_partials = nullptr;   // 64 slots
     uint8_t *d_gt = nullptr;      // 576
     int *d_flags = nullptr;       // [0] pk infinity, [1] is_one
@@ -76,7 +82,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_r); cudaFree(ctx->d_H); cudaFree(ctx->d_Pj); cudaFree(ctx->d_Q);
     cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gt);
-    cudaFree(ctx->d_flags); cudaFree(ctx->d_misc);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i <= ST_COUNT; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
@@ -109,10 +115,15 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     ALLOC(ctx->d_r, n * 8);
     ALLOC(ctx->d_H, n * sizeof(g2_jac));
     ALLOC(ctx->d_Pj, n * sizeof(g1_jac));
-    ALLOC(ctx->d_Q, n * sizeof(g2_aff));
-    ALLOC(ctx->d_P, n * sizeof(g1_aff));
+    ALLOC(ctx->d_Q, (n + 1) * sizeof(g2_aff));            // + the signature-side pair
+    ALLOC(ctx->d_P, (n + 1) * sizeof(g1_aff));
     ALLOC(ctx->d_S, n * sizeof(g2_jac));
-    ALLOC(ctx->d_F, n * sizeof(fp12));
+    ctx->lines_cap = ((n + 1 < LINES_TILE ? n + 1 : LINES_TILE) + 31) & ~(size_t)31;
+    ALLOC(ctx->d_lines, (size_t)ML_NLINES * ML_LINE_WORDS * 4 * ctx->lines_cap);
+    // block products: <= 64 segments x (blocks per tile + 1) x tiles
+    ctx->f_cap = 64 * ((n + 1) / BLS_ACC_BS + 2 + (n + 1) / LINES_TILE + 1);
+    ALLOC(ctx->d_F, ctx->f_cap * sizeof(fp12));
+    ALLOC(ctx->d_seg, 64 * sizeof(fp12));
     ALLOC(ctx->d_partials, 64 * sizeof(fp12));
     ALLOC(ctx->d_gt, 576);
     ALLOC(ctx->d_flags, 4 * sizeof(int));
@@ -167,8 +178,20 @@ static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size
     return 0;
 }
 
-// pairs per Miller-loop thread: share Fp12 squarings when there is parallelism to spare
-static int miller_group(size_t n) { return n >= 65536 ? 4 : (n >= 16384 ? 2 : 1); }
+// Work decomposition of the accumulation: G pairs per group (they share the Fp12 squarings) and nseg loop segments,
+// chosen so that groups x segments gives every SM several warps even for small batches.
+static void miller_shape(size_t np, int &G, int &nseg) {
+    G = 1;
+    while (G < 8 && np / (size_t)(2 * G) >= 8192) G *= 2;
+    size_t ngroups = (np + G - 1) / G;
+    size_t want = ((size_t)1 << 17) / ngroups;
+    nseg = want < 1 ? 1 : (want > 32 ? 32 : (int)want);
+    if (const char *e = getenv("BLSGPU_MILLER_G")) G = atoi(e);
+    if (const char *e = getenv("BLSGPU_MILLER_NSEG")) nseg = atoi(e);
+    if (G < 1) G = 1;
+    if (nseg < 1) nseg = 1;
+    if (nseg > 63) nseg = 63;
+}
 
 // all per-set stages + reductions; leaves the rank partial in d_partials[slot]
 static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t first, size_t total_n,
@@ -179,15 +202,9 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     MARK(ST_SCALARS);
     int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars);
     if (rc) return rc;
-    MARK(ST_HASH);
-    k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
-    MARK(ST_G1MUL);
-    k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
-    MARK(ST_AFFINE);
-    k_pairs_affine<<<nblk(n), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P);
     MARK(ST_G2MUL);
     k_g2_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_S);
-    ctx->launches += 4;
+    ctx->launches++;
     MARK(ST_G2SUM);
     for (size_t m = n; m > 1;) {
         size_t half = (m + 1) / 2;
@@ -195,23 +212,47 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         ctx->launches++;
         m = half;
     }
-    MARK(ST_MILLER);
-    int G = miller_group(n);
-    size_t nf = (n + G - 1) / G;
-    if (G == 4) k_miller<4><<<nblk(nf, 64), 64, 0, s>>>(ctx->d_Q, ctx->d_P, n, ctx->d_F);
-    else if (G == 2) k_miller<2><<<nblk(nf, 64), 64, 0, s>>>(ctx->d_Q, ctx->d_P, n, ctx->d_F);
-    else k_miller<1><<<nblk(nf, 64), 64, 0, s>>>(ctx->d_Q, ctx->d_P, n, ctx->d_F);
+    k_sig_pair<<<1, 32, 0, s>>>(ctx->d_S, n, ctx->d_Q, ctx->d_P);
     ctx->launches++;
-    MARK(ST_GTPROD);
-    for (size_t m = nf; m > 1;) {
-        size_t half = (m + 1) / 2;
-        k_fp12_tree<<<nblk(half), 128, 0, s>>>(ctx->d_F, m, half);
-        ctx->launches++;
-        m = half;
+    MARK(ST_HASH);
+    k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+    MARK(ST_G1MUL);
+    k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
+    MARK(ST_AFFINE);
+    k_pairs_affine<<<nblk(n), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P);
+    ctx->launches += 3;
+    // Miller loop over n + 1 pairs, tile by tile: lines, then per-(group, segment) accumulation
+    const size_t np = n + 1;
+    int G, nseg;
+    miller_shape(np < ctx->lines_cap ? np : ctx->lines_cap, G, nseg);
+    size_t ncols = 0;
+    for (size_t off = 0; off < np; off += ctx->lines_cap) {
+        size_t t = np - off < ctx->lines_cap ? np - off : ctx->lines_cap;
+        ncols += (((t + G - 1) / G) + BLS_ACC_BS - 1) / BLS_ACC_BS;
     }
+    if ((size_t)nseg * ncols > ctx->f_cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "segment product buffer too small");
+    float ms_lines = 0.f, ms_acc = 0.f;
+    size_t col = 0;
+    MARK(ST_LINES);
+    bool single = np <= ctx->lines_cap;
+    for (size_t off = 0; off < np; off += ctx->lines_cap) {
+        size_t t = np - off < ctx->lines_cap ? np - off : ctx->lines_cap;
+        size_t stride = ctx->lines_cap;
+        k_miller_lines<<<nblk(t), 128, 0, s>>>(ctx->d_Q + off, ctx->d_P + off, t, ctx->d_lines, stride);
+        if (single) MARK(ST_ACC);
+        size_t ngroups = (t + G - 1) / G;
+        dim3 grid(nblk(ngroups, BLS_ACC_BS), nseg);
+        k_miller_acc<<<grid, BLS_ACC_BS, 0, s>>>(ctx->d_lines, stride, t, ngroups, G, nseg, ctx->d_F, ncols, col);
+        col += grid.x;
+        ctx->launches += 2;
+    }
+    if (!single) MARK(ST_ACC);                              // multi-tile: lines+acc are reported together under miller_lines
+    (void)ms_lines; (void)ms_acc;
+    MARK(ST_GTPROD);
+    k_fp12_rows<<<nseg, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_seg);
     MARK(ST_PARTIAL);
-    k_partial<<<1, 32, 0, s>>>(ctx->d_S, ctx->d_F, 1, ctx->d_partials + slot);
-    ctx->launches++;
+    k_combine<<<1, 32, 0, s>>>(ctx->d_seg, nseg, ctx->d_partials + slot);
+    ctx->launches += 2;
     MARK(ST_FINAL);
     CK(cudaGetLastError());
     return 0;

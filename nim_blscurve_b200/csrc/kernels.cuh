@@ -6,9 +6,10 @@
 //   k_g1_mul        A5  ec_mult.h:178-223 (G1)                            [r_i] pk_i, Jacobian
 //   k_pairs_affine  A4  e2.c:97-112, e1.c:60-75                           one shared inversion per set
 //   k_g2_mul        A5  ec_mult.h:178-223 (G2)                            [r_i] sig_i ; k_g2_tree sums them
-//   k_miller<G>     A6/A7 pairing.c:220-261                               G pairs per thread share squarings
-//   k_fp12_tree     A8  aggregate.c:410-458 (GT product)
-//   k_partial       A9  aggregate.c:479-495                               conj(ML(S,G1)) * F  -> 576-byte partial
+//   k_sig_pair      A9  aggregate.c:479-495                               (S, -G1) becomes pair number n
+//   k_miller_lines  A7  pairing.c:220-261 (line_dbl/line_add/line_by_Px2) 68 line triples per pair, word-major
+//   k_miller_acc    A6/A7/A8 pairing.c:253-260, aggregate.c:410-458       per (group, segment) Fp12 + block product
+//   k_fp12_rows     A8  GT product per segment row ; k_combine: Horner over segments -> 576-byte rank partial
 //   k_final         A9/A10 pairing.c:371-404, fp12_tower.c:773-786        product, final exp, ==1, GT bytes
 #pragma once
 #include <cuda_runtime.h>
@@ -178,20 +179,94 @@ __global__ void BLS_LB k_fp12_tree(fp12 *F, size_t n, size_t half) {
     F[i] = a;
 }
 
-template <int G>
-__global__ void __launch_bounds__(64, 2 * BLS_LB_BLOCKS) k_miller(const g2_aff *Q, const g1_aff *P, size_t n, fp12 *F) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t base = t * G;
-    if (base >= n) return;
-    int cnt = (n - base) < (size_t)G ? (int)(n - base) : G;
-    g2_aff q[G];
-    g1_aff p[G];
-    g2_jac T[G];
-    fp npx[G];
-    for (int k = 0; k < cnt; k++) { q[k] = Q[base + k]; p[k] = P[base + k]; }
+// ---- split Miller loop (pairing.cuh): lines per pair, then accumulation per (group, segment) ----
+
+// The signature-side pair of aggregate.c:479-495, folded into the multi-Miller product as pair number n:
+// Q[n] = S (affine), P[n] = -G1.  FE(ML(S,-G1)) = FE(conj(ML(S,G1))), so the post-FE GT is unchanged.
+__global__ void k_sig_pair(const g2_jac *S, size_t n, g2_aff *Q, g1_aff *P) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    g2_jac s = *S;
+    g2_aff sa;
+    pt_to_affine(sa, s);                                 // S = infinity -> all-zero -> neutral lines
+    Q[n] = sa;
+    g1_aff g;
+    g.x = G1_GEN_X;
+    fp_neg(g.y, G1_GEN_Y);
+    P[n] = g;
+}
+
+#ifndef BLS_LINES_BLOCKS
+#define BLS_LINES_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, BLS_LINES_BLOCKS) k_miller_lines(const g2_aff *Q, const g1_aff *P, size_t np,
+                                                                       uint32_t *lines, size_t stride) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    g2_aff q = Q[p];
+    g1_aff a = P[p];
+    miller_lines(q, a, lines + p, stride);
+}
+
+#define BLS_ACC_BS 128
+#ifndef BLS_ACC_BLOCKS
+#define BLS_ACC_BLOCKS 2
+#endif
+// product of the block's Fp12 values through shared memory (word-major, conflict-free); result in thread 0
+__device__ __forceinline__ void block_fp12_product(fp12 &f, uint32_t *sm) {
+    const int tid = threadIdx.x;
+    for (int half = BLS_ACC_BS / 2; half >= 1; half >>= 1) {
+        if (tid >= half && tid < 2 * half) {
+            const uint32_t *w = (const uint32_t *)&f;
+            for (int k = 0; k < 144; k++) sm[k * half + (tid - half)] = w[k];
+        }
+        __syncthreads();
+        if (tid < half) {
+            fp12 b;
+            uint32_t *w = (uint32_t *)&b;
+            for (int k = 0; k < 144; k++) w[k] = sm[k * half + tid];
+            fp12_mul(f, f, b);
+        }
+        __syncthreads();
+    }
+}
+
+// grid = (ceil(ngroups / 128), nseg).  Thread (g, j) folds the lines of group g over segment j, the block multiplies
+// its 128 values and writes one Fp12 to Fseg[j * row_stride + col_off + blockIdx.x].
+__global__ void __launch_bounds__(BLS_ACC_BS, BLS_ACC_BLOCKS) k_miller_acc(const uint32_t *lines, size_t stride, size_t np,
+                                                                           size_t ngroups, int G, int nseg, fp12 *Fseg,
+                                                                           size_t row_stride, size_t col_off) {
+    __shared__ uint32_t sm[(BLS_ACC_BS / 2) * 144];
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
     fp12 f;
-    miller_loop_n(f, q, p, cnt, T, npx);
-    F[t] = f;
+    if (g < ngroups) miller_accumulate(f, lines, stride, np, g, ngroups, G, ml_seg_hi(j, nseg), ml_seg_lo(j, nseg));
+    else fp12_set_one(f);
+    block_fp12_product(f, sm);
+    if (threadIdx.x == 0) Fseg[(size_t)j * row_stride + col_off + blockIdx.x] = f;
+}
+
+// one block per segment row: product of ncols values -> seg[j]
+__global__ void __launch_bounds__(BLS_ACC_BS, BLS_ACC_BLOCKS) k_fp12_rows(const fp12 *Fseg, size_t row_stride, size_t ncols,
+                                                                          fp12 *seg) {
+    __shared__ uint32_t sm[(BLS_ACC_BS / 2) * 144];
+    const fp12 *row = Fseg + (size_t)blockIdx.x * row_stride;
+    fp12 f;
+    fp12_set_one(f);
+    bool have = false;
+    for (size_t c = threadIdx.x; c < ncols; c += BLS_ACC_BS) {
+        fp12 b = row[c];
+        if (have) fp12_mul(f, f, b); else { f = b; have = true; }
+    }
+    block_fp12_product(f, sm);
+    if (threadIdx.x == 0) seg[blockIdx.x] = f;
+}
+
+// rank partial = conj(prod_j seg[j]^(2^lo_j))   (single thread; 63 Fp12 squarings)
+__global__ void k_combine(const fp12 *seg, int nseg, fp12 *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    fp12 F;
+    miller_combine(F, seg, nseg);
+    *out = F;
 }
 
 // neutral partial for an empty share: GT one in the in-memory (Montgomery) layout
@@ -204,24 +279,6 @@ __global__ void k_partial_one(fp12 *out, int *flag_out) {
 }
 __global__ void k_copy_flag(const int *src, int *dst) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *dst = *src;
-}
-
-// conj(ML(S, G1)) * F  (aggregate.c:479-495); single thread
-__global__ void k_partial(const g2_jac *S, const fp12 *F, int have_sets, fp12 *out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    g2_jac s = *S;
-    g2_aff sa;
-    pt_to_affine(sa, s);
-    g1_aff g;
-    g.x = G1_GEN_X;
-    g.y = G1_GEN_Y;
-    fp12 gs, f;
-    g2_jac T[1];
-    fp npx[1];
-    miller_loop_n(gs, &sa, &g, 1, T, npx);              // S = infinity -> one (aggregate.c:486-492, pairing.c:233-241)
-    fp12_conj(gs, gs);
-    if (have_sets) { f = *F; fp12_mul(gs, gs, f); }
-    *out = gs;
 }
 
 // prod partials -> final exponentiation -> (== 1), canonical GT bytes

@@ -123,6 +123,122 @@ BLS_NOINLINE void miller_loop_n(fp12 &f, const g2_aff *Q, const g1_aff *P, int n
     fp12_conj(f, f);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split Miller loop: lines first, accumulation second.
+//
+// prod_k f_{|z|,Q_k}(P_k) = prod_i ( prod_k line_{k,i} )^(2^i): the per-pair state (T) only feeds the
+// line coefficients, and the Fp12 accumulator only consumes them.  miller_lines() walks T for ONE pair
+// and emits its 68 sparse line triples (63 tangents + 5 chords, in execution order); miller_accumulate()
+// folds the lines of a GROUP of pairs over a SEGMENT of the loop (bits i_hi..i_lo of |z|) into an Fp12;
+// miller_combine() stitches the per-segment products with the remaining squarings.  The squarings are
+// shared by every pair of a group, the groups and segments are independent work items, and the two
+// halves have half the live state each.
+//
+// Line storage is word-major over pairs ("SoA"): word w (0..71: l0, l1, l2 as 3 x fp2) of line s of pair p
+// lives at lines[(s*72 + w)*stride + p], so that both producers and consumers touch 128 contiguous bytes per warp.
+#define ML_NLINES 68
+#define ML_LINE_WORDS 72
+
+BLS_FN int ml_bit(int i) { return (int)((BLS_Z_ABS >> i) & 1); }
+// index of the tangent line of loop iteration i (i = 62..0); the chord of the same iteration, if any, follows it
+BLS_FN int ml_line_index(int i) { return (62 - i) + (i < 62) + (i < 60) + (i < 57) + (i < 48) + (i < 16); }
+// segment j of nseg covers iterations seg_hi >= i >= seg_lo
+BLS_FN int ml_seg_hi(int j, int nseg) { return 62 - (63 * j) / nseg; }
+BLS_FN int ml_seg_lo(int j, int nseg) { return 62 - (63 * (j + 1)) / nseg + 1; }
+
+BLS_FN void line_store(uint32_t *dst, size_t stride, int s, const fp2 &l0, const fp2 &l1, const fp2 &l2) {
+    uint32_t *d = dst + (size_t)s * ML_LINE_WORDS * stride;
+    for (int w = 0; w < 12; w++) {
+        d[(size_t)w * stride] = l0.c0.l[w];
+        d[(size_t)(12 + w) * stride] = l0.c1.l[w];
+        d[(size_t)(24 + w) * stride] = l1.c0.l[w];
+        d[(size_t)(36 + w) * stride] = l1.c1.l[w];
+        d[(size_t)(48 + w) * stride] = l2.c0.l[w];
+        d[(size_t)(60 + w) * stride] = l2.c1.l[w];
+    }
+}
+
+BLS_FN void line_load(fp2 &l0, fp2 &l1, fp2 &l2, const uint32_t *src, size_t stride, int s) {
+    const uint32_t *d = src + (size_t)s * ML_LINE_WORDS * stride;
+    for (int w = 0; w < 12; w++) {
+        l0.c0.l[w] = d[(size_t)w * stride];
+        l0.c1.l[w] = d[(size_t)(12 + w) * stride];
+        l1.c0.l[w] = d[(size_t)(24 + w) * stride];
+        l1.c1.l[w] = d[(size_t)(36 + w) * stride];
+        l2.c0.l[w] = d[(size_t)(48 + w) * stride];
+        l2.c1.l[w] = d[(size_t)(60 + w) * stride];
+    }
+}
+
+// All 68 lines of one pair, already scaled by (-x_P, y_P).  A pair with P or Q at infinity emits the
+// neutral line (1, 0, 0) everywhere, i.e. contributes 1 to the product (pairing.c:233-241).
+BLS_NOINLINE void miller_lines(const g2_aff &Q, const g1_aff &P, uint32_t *dst, size_t stride) {
+    fp2 l0, l1, l2;
+    if (aff_is_inf(Q) | aff_is_inf(P)) {
+        f_set_one(l0);
+        fp2_set_zero(l1);
+        fp2_set_zero(l2);
+        for (int s = 0; s < ML_NLINES; s++) line_store(dst, stride, s, l0, l1, l2);
+        return;
+    }
+    g2_jac T;
+    pt_from_affine(T, Q);
+    fp npx, py = P.y;
+    fp_neg(npx, P.x);
+    int s = 0;
+    for (int i = 62; i >= 0; i--) {
+        line_dbl(T, l0, l1, l2);
+        fp2_mul_fp(l1, l1, npx);
+        fp2_mul_fp(l2, l2, py);
+        line_store(dst, stride, s++, l0, l1, l2);
+        if (ml_bit(i)) {
+            line_add(T, Q, l0, l1, l2);
+            fp2_mul_fp(l1, l1, npx);
+            fp2_mul_fp(l2, l2, py);
+            line_store(dst, stride, s++, l0, l1, l2);
+        }
+    }
+}
+
+// f = prod over iterations i_hi..i_lo and over the pairs {g, g+ngroups, g+2 ngroups, ...} (at most G, < np)
+// of line^(2^(i-i_lo)); `lines` points at pair 0 of the tile.
+BLS_NOINLINE void miller_accumulate(fp12 &f, const uint32_t *lines, size_t stride, size_t np, size_t g, size_t ngroups,
+                                    int G, int i_hi, int i_lo) {
+    fp2 l0, l1, l2;
+    bool first = true;
+    fp12_set_one(f);
+    for (int i = i_hi; i >= i_lo; i--) {
+        if (!first) fp12_sqr(f, f);
+        const int s = ml_line_index(i), nl = 1 + ml_bit(i);
+        for (int a = 0; a < nl; a++)
+            for (int k = 0; k < G; k++) {
+                size_t p = g + (size_t)k * ngroups;
+                if (p >= np) break;
+                line_load(l0, l1, l2, lines + p, stride, s + a);
+                if (first) {
+                    f.c0.c0 = l0;
+                    f.c0.c1 = l1;
+                    f.c1.c1 = l2;
+                    first = false;
+                } else {
+                    fp12_mul_by_line(f, l0, l1, l2);
+                }
+            }
+    }
+}
+
+// F = conj( prod_j seg[j]^(2^seg_lo(j)) ): Horner over the segments, 63 squarings in total
+BLS_NOINLINE void miller_combine(fp12 &F, const fp12 *seg, int nseg) {
+    fp12 acc = seg[0];
+    for (int j = 1; j < nseg; j++) {
+        int len = ml_seg_hi(j, nseg) - ml_seg_lo(j, nseg) + 1;
+        for (int t = 0; t < len; t++) fp12_sqr(acc, acc);
+        fp12 b = seg[j];
+        fp12_mul(acc, acc, b);
+    }
+    fp12_conj(F, acc);
+}
+
 // r = a^z for a in the cyclotomic subgroup (z negative: conjugate of a^|z|)
 BLS_NOINLINE void cyc_exp_z(fp12 &r, const fp12 &a) {
     fp12 acc = a;

@@ -40,12 +40,13 @@ void hs_final_exp(const fp12 *f, fp12 *r) { final_exp(*r, *f); }
 
 // whole batch-verification pipeline as the kernels of kernels.cuh sequence it, executed on the host
 struct hs_sigset { g1_aff pk; uint8_t msg[32]; g2_aff sig; };
-int hs_batch_verify(const hs_sigset *sets, size_t n, const uint64_t *r, int group, uint8_t *gt_out) {
+int hs_batch_verify(const hs_sigset *sets, size_t n, const uint64_t *r, int group, int nseg, uint8_t *gt_out) {
     static const uint8_t dst[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_";
     memset(gt_out, 0, 576);
     if (n == 0) return 0;
-    g2_aff *Q = new g2_aff[n];
-    g1_aff *P = new g1_aff[n];
+    const size_t np = n + 1;                       // + the signature-side pair (S, -G1)
+    g2_aff *Q = new g2_aff[np];
+    g1_aff *P = new g1_aff[np];
     g2_jac S; pt_set_inf(S);
     int pk_inf = 0;
     for (size_t i = 0; i < n; i++) {
@@ -57,22 +58,29 @@ int hs_batch_verify(const hs_sigset *sets, size_t n, const uint64_t *r, int grou
         g2_jac sj; pt_mul_u64(sj, sets[i].sig, r[i]);
         pt_add(S, S, sj);
     }
-    fp12 F; fp12_set_one(F);
-    for (size_t base = 0; base < n; base += group) {
-        int cnt = (int)((n - base) < (size_t)group ? (n - base) : (size_t)group);
-        g2_jac T[8]; fp npx[8]; fp12 f;
-        miller_loop_n(f, Q + base, P + base, cnt, T, npx);
-        fp12_mul(F, F, f);
+    pt_to_affine(Q[n], S);
+    P[n].x = G1_GEN_X;
+    fp_neg(P[n].y, G1_GEN_Y);
+    // kernel L: lines of every pair, word-major over pairs
+    const size_t stride = (np + 31) & ~(size_t)31;
+    uint32_t *lines = new uint32_t[(size_t)ML_NLINES * ML_LINE_WORDS * stride];
+    for (size_t p = 0; p < np; p++) miller_lines(Q[p], P[p], lines + p, stride);
+    // kernel A + row products: one Fp12 per segment
+    const size_t ngroups = (np + group - 1) / group;
+    fp12 *seg = new fp12[nseg];
+    for (int j = 0; j < nseg; j++) {
+        fp12_set_one(seg[j]);
+        for (size_t g = 0; g < ngroups; g++) {
+            fp12 f;
+            miller_accumulate(f, lines, stride, np, g, ngroups, group, ml_seg_hi(j, nseg), ml_seg_lo(j, nseg));
+            fp12_mul(seg[j], seg[j], f);
+        }
     }
-    g2_aff sa; pt_to_affine(sa, S);
-    g1_aff g; g.x = G1_GEN_X; g.y = G1_GEN_Y;
-    fp12 gs; g2_jac T[1]; fp npx[1];
-    miller_loop_n(gs, &sa, &g, 1, T, npx);
-    fp12_conj(gs, gs);
-    fp12_mul(gs, gs, F);
-    fp12 gt; final_exp(gt, gs);
+    fp12 F, gt;
+    miller_combine(F, seg, nseg);
+    final_exp(gt, F);
     fp12_to_bytes(gt_out, gt);
-    delete[] Q; delete[] P;
+    delete[] Q; delete[] P; delete[] lines; delete[] seg;
     if (pk_inf) { memset(gt_out, 0, 576); return 0; }
     return fp12_is_one(gt) ? 1 : 0;
 }

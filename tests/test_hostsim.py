@@ -136,14 +136,14 @@ def test_tower(hs):
         assert f12f(bytes(r)) == pr.final_exp(a)
 
 
-@pytest.mark.parametrize("group", [1, 4])
-def test_batch_pipeline_golden(hs, group):
+@pytest.mark.parametrize("group,nseg", [(1, 1), (4, 8), (3, 5), (8, 63)])
+def test_batch_pipeline_golden(hs, group, nseg):
     d = json.load(open(os.path.join(GOLD, "batch_scenarios.json")))
     for s in d["scenarios"]:
         raw = bytes.fromhex(s["sets"])
         sc = (C.c_uint64 * s["n"])(*[int(x) for x in s["scalars"]])
         gt = out(576)
-        ok = hs.hs_batch_verify(buf(raw), C.c_size_t(s["n"]), sc, group, gt)
+        ok = hs.hs_batch_verify(buf(raw), C.c_size_t(s["n"]), sc, group, nseg, gt)
         assert bool(ok) == s["ok"], s["name"]
         if s["name"] != "infinite_pubkey":
             assert bytes(gt).hex() == s["gt"], s["name"]
