@@ -115,6 +115,14 @@ int blsgpu_msm_g1(blsgpu_ctx *ctx, const void *points96, const void *scalars, si
 int blsgpu_msm_g1_dev(blsgpu_ctx *ctx, const void *d_points96, const void *d_scalars, size_t n, size_t nbits,
                       uint8_t out96[96]);
 
+/* G2 multi-scalar multiplication (replaces blst_p2s_mult_pippenger + blst_p2_to_affine,
+ * vendor/blst/src/multi_scalar.c:442-446; with nbits = 64 this is the signature half of
+ * MultiSignatureSet.combine, blst_min_pubkey_sig_core.nim:637-644): points n x 192 bytes affine. */
+int blsgpu_msm_g2(blsgpu_ctx *ctx, const void *points192, const void *scalars, size_t n, size_t nbits,
+                  uint8_t out192[192]);
+int blsgpu_msm_g2_dev(blsgpu_ctx *ctx, const void *d_points192, const void *d_scalars, size_t n, size_t nbits,
+                      uint8_t out192[192]);
+
 /* Per-stage device times (ms) of the last batch_verify/partial call on this context, measured with CUDA
  * events on the call's stream.  Returns the number of stages written (<= max); names via blsgpu_stage_name. */
 int blsgpu_last_stage_ms(const blsgpu_ctx *ctx, float *ms, int max);

@@ -163,6 +163,16 @@ def msmG1(cache: BatchedBLSVerifierCache, points96: bytes, scalars: bytes, nbits
     return bytes(out)
 
 
+def msmG2(cache: BatchedBLSVerifierCache, points192: bytes, scalars: bytes, nbits: int = 255) -> bytes:
+    """sum_i [k_i] Q_i in G2, affine (blst_p2s_mult_pippenger + to_affine; multi_scalar.c:442-446)."""
+    n = len(points192) // 192
+    out = (C.c_uint8 * 192)()
+    rc = lib().blsgpu_msm_g2(cache.handle, points192, scalars, n, nbits, out)
+    if rc < 0:
+        raise BlsGpuError(f"msm_g2 failed ({rc}): {cache.last_error()}")
+    return bytes(out)
+
+
 def rlcScalars(cache: BatchedBLSVerifierCache, srb: bytes, n: int, chunks: int):
     out = (C.c_uint64 * n)()
     rc = lib().blsgpu_rlc_scalars(cache.handle, srb, n, chunks, out)

@@ -2,6 +2,7 @@
 // Everything that computes runs in the kernels of kernels.cuh / msm.cuh; this file only moves bytes and
 // launches.  There is no CPU implementation of any operation behind these entry points.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -41,6 +42,7 @@ struct blsgpu_ctx {
     int *d_flags = nullptr;       // [0] pk infinity, [1] is_one
     void *d_misc = nullptr;       // scratch for aggregate / hash API
     size_t misc_bytes = 0;
+    void *d_misc2 = nullptr;      // small result scratch (MSM output)
     uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
     cudaEvent_t ev[ST_COUNT + 1];
     bool ev_valid[ST_COUNT + 1];
@@ -82,7 +84,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_r); cudaFree(ctx->d_H); cudaFree(ctx->d_Pj); cudaFree(ctx->d_Q);
     cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gt);
-    cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i <= ST_COUNT; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
@@ -152,6 +154,12 @@ static int ensure_misc(blsgpu_ctx *ctx, size_t bytes) {
     return 0;
 }
 
+static int ensure_misc2(blsgpu_ctx *ctx, size_t bytes) {
+    if (ctx->d_misc2) return 0;
+    CK(cudaMalloc(&ctx->d_misc2, bytes < 1024 ? 1024 : bytes));
+    return 0;
+}
+
 static words8 words_of(const uint8_t b[32]) {
     words8 w;
     for (int i = 0; i < 8; i++)
@@ -203,14 +211,25 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars);
     if (rc) return rc;
     MARK(ST_G2MUL);
-    k_g2_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_S);
-    ctx->launches++;
-    MARK(ST_G2SUM);
-    for (size_t m = n; m > 1;) {
-        size_t half = (m + 1) / 2;
-        k_g2_tree<<<nblk(half), 128, 0, s>>>(ctx->d_S, m, half);
+    // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
+    // buckets, n independent 64-bit multiplications + tree below that
+    static const size_t g2_msm_min = getenv("BLSGPU_G2_MSM_MIN") ? (size_t)atoll(getenv("BLSGPU_G2_MSM_MIN")) : 2048;
+    if (n >= g2_msm_min) {
+        std::string err;
+        rc = msm_run<fp2>(ctx->msm, (const uint8_t *)d_sets + offsetof(sigset, sig), sizeof(sigset), (const uint8_t *)ctx->d_r, 8,
+                          n, 64, s, ctx->d_S, nullptr, &ctx->launches, err);
+        if (rc) return fail(ctx, rc == -1 ? BLSGPU_ERR_CUDA : BLSGPU_ERR_ARG, err.c_str());
+        MARK(ST_G2SUM);
+    } else {
+        k_g2_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_S);
         ctx->launches++;
-        m = half;
+        MARK(ST_G2SUM);
+        for (size_t m = n; m > 1;) {
+            size_t half = (m + 1) / 2;
+            k_g2_tree<<<nblk(half), 128, 0, s>>>(ctx->d_S, m, half);
+            ctx->launches++;
+            m = half;
+        }
     }
     k_sig_pair<<<1, 32, 0, s>>>(ctx->d_S, n, ctx->d_Q, ctx->d_P);
     ctx->launches++;
@@ -231,7 +250,6 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         ncols += (((t + G - 1) / G) + BLS_ACC_BS - 1) / BLS_ACC_BS;
     }
     if ((size_t)nseg * ncols > ctx->f_cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "segment product buffer too small");
-    float ms_lines = 0.f, ms_acc = 0.f;
     size_t col = 0;
     MARK(ST_LINES);
     bool single = np <= ctx->lines_cap;
@@ -247,7 +265,6 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         ctx->launches += 2;
     }
     if (!single) MARK(ST_ACC);                              // multi-tile: lines+acc are reported together under miller_lines
-    (void)ms_lines; (void)ms_acc;
     MARK(ST_GTPROD);
     k_fp12_rows<<<nseg, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_seg);
     MARK(ST_PARTIAL);
@@ -474,35 +491,59 @@ extern "C" int blsgpu_aggregate_g2(blsgpu_ctx *ctx, const void *points192, size_
     return 1;
 }
 
-extern "C" int blsgpu_msm_g1_dev(blsgpu_ctx *ctx, const void *d_points96, const void *d_scalars, size_t n, size_t nbits,
-                                 uint8_t out96[96]) {
-    if (!ctx || !out96) return BLSGPU_ERR_ARG;
-    memset(out96, 0, 96);
+template <class F>
+static int msm_api_dev(blsgpu_ctx *ctx, const void *d_points, const void *d_scalars, size_t n, size_t nbits, uint8_t *out) {
+    const size_t pb = sizeof(aff_t<F>);
+    if (!ctx || !out) return BLSGPU_ERR_ARG;
+    memset(out, 0, pb);
     if (n == 0) return 0;
-    if (!d_points96 || !d_scalars || nbits == 0 || nbits > 256) return fail(ctx, BLSGPU_ERR_ARG, "bad MSM arguments");
+    if (!d_points || !d_scalars || nbits == 0 || nbits > 256) return fail(ctx, BLSGPU_ERR_ARG, "bad MSM arguments");
     CK(cudaSetDevice(ctx->device));
+    int rc = ensure_misc2(ctx, 256);
+    if (rc) return rc;
     std::string err;
-    int rc = msm_g1_run(ctx->msm, (const g1_aff *)d_points96, (const uint8_t *)d_scalars, n, (int)nbits, ctx->stream,
-                        ctx->h_pinned, err);
-    if (rc) return fail(ctx, rc, err.c_str());
-    memcpy(out96, ctx->h_pinned, 96);
+    ctx->launches = 0;
+    rc = msm_run<F>(ctx->msm, (const uint8_t *)d_points, pb, (const uint8_t *)d_scalars, (nbits + 7) / 8, n, (int)nbits,
+                    ctx->stream, nullptr, (aff_t<F> *)ctx->d_misc2, &ctx->launches, err);
+    if (rc) return fail(ctx, rc == -1 ? BLSGPU_ERR_CUDA : BLSGPU_ERR_ARG, err.c_str());
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_misc2, pb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->h_pinned, pb);
     return 1;
 }
 
-extern "C" int blsgpu_msm_g1(blsgpu_ctx *ctx, const void *points96, const void *scalars, size_t n, size_t nbits,
-                             uint8_t out96[96]) {
-    if (!ctx || !out96) return BLSGPU_ERR_ARG;
-    memset(out96, 0, 96);
+template <class F>
+static int msm_api_host(blsgpu_ctx *ctx, const void *points, const void *scalars, size_t n, size_t nbits, uint8_t *out) {
+    const size_t pb = sizeof(aff_t<F>);
+    if (!ctx || !out) return BLSGPU_ERR_ARG;
+    memset(out, 0, pb);
     if (n == 0) return 0;
-    if (!points96 || !scalars || nbits == 0 || nbits > 256) return fail(ctx, BLSGPU_ERR_ARG, "bad MSM arguments");
+    if (!points || !scalars || nbits == 0 || nbits > 256) return fail(ctx, BLSGPU_ERR_ARG, "bad MSM arguments");
     CK(cudaSetDevice(ctx->device));
     size_t sb = (nbits + 7) / 8;
-    int rc = ensure_misc(ctx, n * 96 + n * sb + 256);
+    int rc = ensure_misc(ctx, n * pb + n * sb + 256);
     if (rc) return rc;
     uint8_t *base = (uint8_t *)ctx->d_misc;
-    CK(cudaMemcpyAsync(base, points96, n * 96, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(base + n * 96, scalars, n * sb, cudaMemcpyHostToDevice, ctx->stream));
-    return blsgpu_msm_g1_dev(ctx, base, base + n * 96, n, nbits, out96);
+    CK(cudaMemcpyAsync(base, points, n * pb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(base + n * pb, scalars, n * sb, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_api_dev<F>(ctx, base, base + n * pb, n, nbits, out);
+}
+
+extern "C" int blsgpu_msm_g1_dev(blsgpu_ctx *ctx, const void *d_points96, const void *d_scalars, size_t n, size_t nbits,
+                                 uint8_t out96[96]) {
+    return msm_api_dev<fp>(ctx, d_points96, d_scalars, n, nbits, out96);
+}
+extern "C" int blsgpu_msm_g1(blsgpu_ctx *ctx, const void *points96, const void *scalars, size_t n, size_t nbits,
+                             uint8_t out96[96]) {
+    return msm_api_host<fp>(ctx, points96, scalars, n, nbits, out96);
+}
+extern "C" int blsgpu_msm_g2_dev(blsgpu_ctx *ctx, const void *d_points192, const void *d_scalars, size_t n, size_t nbits,
+                                 uint8_t out192[192]) {
+    return msm_api_dev<fp2>(ctx, d_points192, d_scalars, n, nbits, out192);
+}
+extern "C" int blsgpu_msm_g2(blsgpu_ctx *ctx, const void *points192, const void *scalars, size_t n, size_t nbits,
+                             uint8_t out192[192]) {
+    return msm_api_host<fp2>(ctx, points192, scalars, n, nbits, out192);
 }
 
 extern "C" int blsgpu_msm_make_inputs(blsgpu_ctx *ctx, uint64_t seed, size_t n, void *d_points96, void *d_scalars32) {

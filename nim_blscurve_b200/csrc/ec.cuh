@@ -239,7 +239,9 @@ template <class F> BLS_NOINLINE void pt_mul_u64(jac_t<F> &r, const aff_t<F> &p, 
 template <class F> BLS_NOINLINE void pt_mul_words(jac_t<F> &r, const jac_t<F> &p, const uint32_t *k, int nwords) {
     jac_t<F> acc;
     pt_set_inf(acc);
-    for (int i = nwords * 32 - 1; i >= 0; i--) {
+    int i = nwords * 32 - 1;
+    while (i >= 0 && !((k[i >> 5] >> (i & 31)) & 1)) i--;      // skip leading zero bits
+    for (; i >= 0; i--) {
         pt_dbl(acc, acc);
         if ((k[i >> 5] >> (i & 31)) & 1) pt_add(acc, acc, p);
     }

@@ -1,16 +1,23 @@
-// msm.cuh — G1 multi-scalar multiplication: signed-digit Pippenger with a sorted bucket scatter.
-// Restates the result of blst_p1s_mult_pippenger (vendor/blst/src/multi_scalar.c:415-434; window loop
-// :370-397, tile :332-368, bucket integration :295-311) — the affine sum  sum_i [k_i] P_i  is canonical,
+// msm.cuh — multi-scalar multiplication in G1 and G2: signed-digit Pippenger with a sorted bucket scatter.
+// Restates the results of blst_p1s_mult_pippenger / blst_p2s_mult_pippenger (vendor/blst/src/multi_scalar.c:415-446;
+// window loop :370-397, tile :332-368, bucket integration :295-311) — the affine sum  sum_i [k_i] P_i  is canonical,
 // so the GPU decomposition is free to differ:
 //   1. k_msm_count    signed window digits (Booth-style carry, digits in (-2^(c-1), 2^(c-1)]), histogram
 //                     of (window, |digit|) with global atomics
-//   2. k_msm_scan     exclusive prefix sum of the histogram (one block)
+//   2. k_msm_scan     exclusive prefix sums of the histogram and of the per-bucket task counts (one block)
 //   3. k_msm_scatter  counting-sort scatter of (point index, sign) into bucket order
-//   4. k_msm_bucket   one thread per (window, bucket): gathers its points, mixed Jacobian additions
-//   5. k_msm_segment  running-sum integration of 32-bucket segments, weighted by the segment base
-//   6. k_g1_tree_rows per-window tree sum of the segment results
-//   7. k_msm_horner   Horner over windows (c doublings each), to affine
-// Scalars are NOT reduced mod r (as in the reference); nbits low bits of each little-endian scalar are used.
+//   4. k_msm_task     one thread per TASK = at most `ch` consecutive entries of one bucket: gathers its points,
+//                     mixed Jacobian additions -> one partial per task (a bucket of any size is split evenly,
+//                     so a skewed digit distribution cannot serialise the kernel)
+//   5. k_msm_combine  one thread per bucket sums its partials; buckets with more than MSM_BIG partials are
+//                     deferred to k_msm_combine_big (one warp per bucket, shuffle tree)
+//   6. k_msm_segment  running-sum integration of L-bucket segments, weighted by the segment base
+//   7. k_tree_rows    per-window tree sum of the segment results
+//   8. k_msm_horner   Horner over windows (c doublings each), Jacobian and/or affine output
+// The same kernels serve the batch verifier's sum  S = sum_i [r_i] sig_i  (G2, 64-bit scalars, points read in place
+// from the SignatureSet array) — vendor/blst/src/aggregate.c:321-335 accumulates that sum one scalar
+// multiplication at a time.
+// Scalars are NOT reduced mod r (as in the reference); the nbits low bits of each little-endian scalar are used.
 #pragma once
 #include <string>
 #include "kernels.cuh"
@@ -28,7 +35,7 @@ static inline void msm_free(msm_state &m) {
     m.bytes = 0;
 }
 
-#define MSM_SEG 32
+#define MSM_BIG 32
 
 // signed digit of window w (width c) of the nbits-bit little-endian scalar at sc (sb bytes)
 __device__ __forceinline__ int msm_digit(const uint8_t *sc, int sb, int nbits, int c, int w, int &carry) {
@@ -52,11 +59,11 @@ __device__ __forceinline__ int msm_digit(const uint8_t *sc, int sb, int nbits, i
     return d;
 }
 
-__global__ void __launch_bounds__(256) k_msm_count(const uint8_t *scalars, size_t n, int sb, int nbits, int c, int nwin,
-                                                   uint32_t *counts) {
+__global__ void __launch_bounds__(256) k_msm_count(const uint8_t *scalars, size_t sstride, size_t n, int sb, int nbits, int c,
+                                                   int nwin, uint32_t *counts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint8_t *sc = scalars + i * sb;
+    const uint8_t *sc = scalars + i * sstride;
     int carry = 0;
     const uint32_t B = 1u << (c - 1);
     for (int w = 0; w < nwin; w++) {
@@ -65,45 +72,47 @@ __global__ void __launch_bounds__(256) k_msm_count(const uint8_t *scalars, size_
     }
 }
 
-// exclusive scan of m counters into offsets[0..m] (offsets[m] = total); single block of 1024 threads
-__global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *counts, size_t m, uint32_t *offsets, uint32_t *cursor) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+// Exclusive scans over m buckets (single block of 1024 threads):
+//   offsets[0..m] of the entry counts (cursor = a working copy for the scatter), toff[0..m] of ceil(count / ch).
+__global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *counts, size_t m, uint32_t ch, uint32_t *offsets,
+                                                   uint32_t *cursor, uint32_t *toff) {
+    __shared__ uint32_t ws[2][32];
+    __shared__ uint32_t carry_s[2];
+    if (threadIdx.x < 2) carry_s[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (size_t base = 0; base < m; base += 1024) {
         size_t i = base + threadIdx.x;
-        uint32_t v = i < m ? counts[i] : 0, x = v;
+        uint32_t v0 = i < m ? counts[i] : 0, v1 = (v0 + ch - 1) / ch, x0 = v0, x1 = v1;
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+            if (lane >= o) { x0 += y0; x1 += y1; }
         }
-        if (lane == 31) warp_sums[wid] = x;
+        if (lane == 31) { ws[0][wid] = x0; ws[1][wid] = x1; }
         __syncthreads();
-        if (wid == 0) {
-            uint32_t s = warp_sums[lane], t = s;
+        if (wid < 2) {
+            uint32_t s = ws[wid][lane], t = s;
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
                 if (lane >= o) t += y;
             }
-            warp_sums[lane] = t - s;      // exclusive warp offsets
+            ws[wid][lane] = t - s;        // exclusive warp offsets
         }
         __syncthreads();
-        uint32_t excl = carry_s + warp_sums[wid] + x - v;
-        if (i < m) { offsets[i] = excl; cursor[i] = excl; }
+        uint32_t e0 = carry_s[0] + ws[0][wid] + x0 - v0, e1 = carry_s[1] + ws[1][wid] + x1 - v1;
+        if (i < m) { offsets[i] = e0; cursor[i] = e0; toff[i] = e1; }
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = excl + v;
+        if (threadIdx.x == 1023) { carry_s[0] = e0 + v0; carry_s[1] = e1 + v1; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) offsets[m] = carry_s;
+    if (threadIdx.x == 0) { offsets[m] = carry_s[0]; toff[m] = carry_s[1]; }
 }
 
-__global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *scalars, size_t n, int sb, int nbits, int c, int nwin,
-                                                     uint32_t *cursor, uint32_t *entries) {
+__global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *scalars, size_t sstride, size_t n, int sb, int nbits, int c,
+                                                     int nwin, uint32_t *cursor, uint32_t *entries) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint8_t *sc = scalars + i * sb;
+    const uint8_t *sc = scalars + i * sstride;
     int carry = 0;
     const uint32_t B = 1u << (c - 1);
     for (int w = 0; w < nwin; w++) {
@@ -115,43 +124,98 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *scalars, siz
     }
 }
 
-__global__ void BLS_LB k_msm_bucket(const g1_aff *points, const uint32_t *offsets, const uint32_t *entries,
-                                                    size_t nbuckets, g1_jac *buckets) {
-    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nbuckets) return;
-    uint32_t lo = offsets[g], hi = offsets[g + 1];
-    g1_jac acc;
+// task t -> (bucket b, chunk): toff[b] <= t < toff[b+1]; sums entries [offsets[b] + chunk*ch, ... + ch) of bucket b
+template <class F>
+__global__ void BLS_LB k_msm_task(const uint8_t *points, size_t pstride, const uint32_t *offsets, const uint32_t *toff,
+                                  const uint32_t *entries, size_t nb, uint32_t ch, jac_t<F> *partials) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= toff[nb]) return;
+    size_t lo = 0, hi = nb;                        // largest b with toff[b] <= t
+    while (hi - lo > 1) {
+        size_t mid = (lo + hi) >> 1;
+        if (toff[mid] <= t) lo = mid; else hi = mid;
+    }
+    const size_t b = lo;
+    uint32_t e0 = offsets[b] + (uint32_t)(t - toff[b]) * ch, e1 = offsets[b + 1];
+    if (e1 > e0 + ch) e1 = e0 + ch;
+    jac_t<F> acc;
     pt_set_inf(acc);
-    for (uint32_t e = lo; e < hi; e++) {
+    for (uint32_t e = e0; e < e1; e++) {
         uint32_t ent = entries[e];
-        g1_aff p = points[ent >> 1];
-        if (ent & 1) fp_neg(p.y, p.y);
+        aff_t<F> p = *(const aff_t<F> *)(points + (size_t)(ent >> 1) * pstride);
+        if (ent & 1) f_neg(p.y, p.y);
         pt_add_affine(acc, acc, p);
     }
-    buckets[g] = acc;
+    partials[t] = acc;
 }
 
-// segment j of window w covers digit magnitudes b in [j*SEG+1, j*SEG+SEG] (bucket index b-1):
-//   T = sum_b (b - j*SEG) B_b  +  [j*SEG] sum_b B_b
-__global__ void BLS_LB k_msm_segment(const g1_jac *buckets, int c, int nwin, g1_jac *segs) {
+template <class F>
+__global__ void BLS_LB k_msm_combine(const jac_t<F> *partials, const uint32_t *toff, size_t nb, jac_t<F> *buckets,
+                                     uint32_t *biglist, uint32_t *bigcount) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t t0 = toff[b], t1 = toff[b + 1];
+    if (t1 - t0 > MSM_BIG) {
+        biglist[atomicAdd(bigcount, 1u)] = (uint32_t)b;
+        return;
+    }
+    jac_t<F> acc;
+    pt_set_inf(acc);
+    if (t1 > t0) acc = partials[t0];
+    for (uint32_t t = t0 + 1; t < t1; t++) {
+        jac_t<F> x = partials[t];
+        pt_add(acc, acc, x);
+    }
+    buckets[b] = acc;
+}
+
+// one warp per over-full bucket: lanes stride over its partials, then a shuffle tree
+template <class F>
+__global__ void BLS_LB k_msm_combine_big(const jac_t<F> *partials, const uint32_t *toff, const uint32_t *biglist,
+                                         const uint32_t *bigcount, jac_t<F> *buckets) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t nbig = *bigcount;
+    for (size_t i = warp; i < nbig; i += nwarps) {
+        const uint32_t b = biglist[i], t0 = toff[b], t1 = toff[b + 1];
+        jac_t<F> acc;
+        pt_set_inf(acc);
+        for (uint32_t t = t0 + lane; t < t1; t += 32) {
+            jac_t<F> x = partials[t];
+            pt_add(acc, acc, x);
+        }
+        for (int o = 16; o >= 1; o >>= 1) {
+            jac_t<F> other;
+            uint32_t *dst = (uint32_t *)&other;
+            const uint32_t *src = (const uint32_t *)&acc;
+            for (int k = 0; k < (int)(sizeof(jac_t<F>) / 4); k++) dst[k] = __shfl_down_sync(0xffffffffu, src[k], o);
+            pt_add(acc, acc, other);
+        }
+        if (lane == 0) buckets[b] = acc;
+    }
+}
+
+// segment j of window w covers digit magnitudes b in [j*L+1, j*L+L] (bucket index b-1):
+//   T = sum_b (b - j*L) B_b  +  [j*L] sum_b B_b
+template <class F>
+__global__ void BLS_LB k_msm_segment(const jac_t<F> *buckets, int c, int nwin, uint32_t L, jac_t<F> *segs) {
     const uint32_t B = 1u << (c - 1);
-    const uint32_t L = B < MSM_SEG ? B : MSM_SEG;
     const uint32_t nseg = B / L;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)nwin * nseg) return;
     uint32_t w = (uint32_t)(t / nseg), j = (uint32_t)(t % nseg);
-    const g1_jac *bk = buckets + (size_t)w * B + (size_t)j * L;
-    g1_jac running, acc;
+    const jac_t<F> *bk = buckets + (size_t)w * B + (size_t)j * L;
+    jac_t<F> running, acc;
     pt_set_inf(running);
     pt_set_inf(acc);
     for (int b = (int)L - 1; b >= 0; b--) {
-        g1_jac x = bk[b];
+        jac_t<F> x = bk[b];
         pt_add(running, running, x);
         pt_add(acc, acc, running);
     }
     uint32_t k = j * L;
     if (k) {
-        g1_jac m;
+        jac_t<F> m;
         pt_mul_words(m, running, &k, 1);
         pt_add(acc, acc, m);
     }
@@ -159,27 +223,32 @@ __global__ void BLS_LB k_msm_segment(const g1_jac *buckets, int c, int nwin, g1_
 }
 
 // row-wise pairwise tree step over `rows` rows of `stride` entries
-__global__ void BLS_LB k_g1_tree_rows(g1_jac *S, int rows, size_t stride, size_t m, size_t half) {
+template <class F>
+__global__ void BLS_LB k_tree_rows(jac_t<F> *S, int rows, size_t stride, size_t m, size_t half) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)rows * half) return;
     size_t r = t / half, i = t % half;
     if (i + half >= m) return;
-    g1_jac a = S[r * stride + i], b = S[r * stride + i + half];
+    jac_t<F> a = S[r * stride + i], b = S[r * stride + i + half];
     pt_add(a, a, b);
     S[r * stride + i] = a;
 }
 
-__global__ void k_msm_horner(const g1_jac *W, size_t stride, int nwin, int c, g1_aff *out) {
+template <class F>
+__global__ void k_msm_horner(const jac_t<F> *W, size_t stride, int nwin, int c, jac_t<F> *out_jac, aff_t<F> *out_aff) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    g1_jac acc = W[(size_t)(nwin - 1) * stride];
+    jac_t<F> acc = W[(size_t)(nwin - 1) * stride];
     for (int w = nwin - 2; w >= 0; w--) {
         for (int k = 0; k < c; k++) pt_dbl(acc, acc);
-        g1_jac x = W[(size_t)w * stride];
+        jac_t<F> x = W[(size_t)w * stride];
         pt_add(acc, acc, x);
     }
-    g1_aff a;
-    pt_to_affine(a, acc);
-    *out = a;
+    if (out_jac) *out_jac = acc;
+    if (out_aff) {
+        aff_t<F> a;
+        pt_to_affine(a, acc);
+        *out_aff = a;
+    }
 }
 
 // synthetic MSM inputs (benchmark only): P_i = [k_i]G1 with a 96-bit k_i, 255-bit coefficients
@@ -208,65 +277,88 @@ __global__ void BLS_LB k_msm_make_inputs(uint64_t seed, size_t n, g1_aff *points
     scalars[32 * i + 31] &= 0x7f;
 }
 
-static inline int msm_window_bits(size_t n) {
+// window width: ~log2(n) - 4, then the smallest width that needs the same number of windows
+static inline void msm_shape(size_t n, int nbits, int &c, int &nwin) {
     int lg = 0;
     while ((n >> (lg + 1)) != 0) lg++;
-    int c = lg - 4;
+    c = lg - 4;
     if (c < 2) c = 2;
     if (c > 16) c = 16;
-    return c;
+    nwin = (nbits + 1 + c - 1) / c;
+    c = (nbits + 1 + nwin - 1) / nwin;
+    if (c < 2) c = 2;
 }
 
-// d_points / d_scalars are device pointers; the affine result lands in h_out (pinned, 96 bytes)
-static inline int msm_g1_run(msm_state &st, const g1_aff *d_points, const uint8_t *d_scalars, size_t n, int nbits,
-                             cudaStream_t s, uint8_t *h_out, std::string &err) {
+// Stream-ordered: d_points (stride pstride bytes, aff_t<F> each) and d_scalars (stride sstride bytes, little-endian,
+// nbits bits used) are device pointers; the sum lands in d_out_jac and/or d_out_aff (device, either may be null).
+// No host synchronisation unless the scratch buffer has to grow.
+template <class F>
+static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride, const uint8_t *d_scalars, size_t sstride,
+                          size_t n, int nbits, cudaStream_t s, jac_t<F> *d_out_jac, aff_t<F> *d_out_aff, int *launches,
+                          std::string &err) {
+    typedef jac_t<F> J;
     if (n >= ((size_t)1 << 31)) { err = "msm: too many points"; return -2; }
     const int sb = (nbits + 7) / 8;
-    const int c = msm_window_bits(n);
-    const int nwin = (nbits + 1 + c - 1) / c;
+    int c, nwin;
+    msm_shape(n, nbits, c, nwin);
     const size_t B = (size_t)1 << (c - 1);
     const size_t nb = (size_t)nwin * B;
-    const size_t L = B < MSM_SEG ? B : MSM_SEG;
+    const uint32_t ch = sizeof(F) == sizeof(fp) ? 32 : 16;
+    size_t L = B / 512;                            // segment length: short serial chains, <= 512 segments per window
+    if (L < 4) L = 4;
+    if (L > 32) L = 32;
+    if (L > B) L = B;
     const size_t nseg = B / L;
+    const size_t tmax = n * (size_t)nwin / ch + nb + 1;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o_counts = 0;
     size_t o_offsets = o_counts + al(nb * 4);
     size_t o_cursor = o_offsets + al((nb + 1) * 4);
-    size_t o_entries = o_cursor + al(nb * 4);
-    size_t o_buckets = o_entries + al(n * (size_t)nwin * 4);
-    size_t o_segs = o_buckets + al(nb * sizeof(g1_jac));
-    size_t o_out = o_segs + al((size_t)nwin * nseg * sizeof(g1_jac));
-    size_t total = o_out + 256;
+    size_t o_toff = o_cursor + al(nb * 4);
+    size_t o_big = o_toff + al((nb + 1) * 4);
+    size_t o_bigcount = o_big + al(nb * 4);
+    size_t o_entries = o_bigcount + 256;
+    size_t o_partials = o_entries + al(n * (size_t)nwin * 4);
+    size_t o_buckets = o_partials + al(tmax * sizeof(J));
+    size_t o_segs = o_buckets + al(nb * sizeof(J));
+    size_t total = o_segs + al((size_t)nwin * nseg * sizeof(J));
     cudaError_t e;
 #define MCK(call) if ((e = (call)) != cudaSuccess) { err = std::string(#call ": ") + cudaGetErrorString(e); return -1; }
     if (st.bytes < total) {
-        if (st.buf) cudaFree(st.buf);
+        if (st.buf) { MCK(cudaStreamSynchronize(s)); cudaFree(st.buf); }
         st.buf = nullptr;
         st.bytes = 0;
         MCK(cudaMalloc((void **)&st.buf, total));
         st.bytes = total;
     }
     uint32_t *counts = (uint32_t *)(st.buf + o_counts), *offsets = (uint32_t *)(st.buf + o_offsets);
-    uint32_t *cursor = (uint32_t *)(st.buf + o_cursor), *entries = (uint32_t *)(st.buf + o_entries);
-    g1_jac *buckets = (g1_jac *)(st.buf + o_buckets), *segs = (g1_jac *)(st.buf + o_segs);
-    g1_aff *d_out = (g1_aff *)(st.buf + o_out);
+    uint32_t *cursor = (uint32_t *)(st.buf + o_cursor), *toff = (uint32_t *)(st.buf + o_toff);
+    uint32_t *biglist = (uint32_t *)(st.buf + o_big), *bigcount = (uint32_t *)(st.buf + o_bigcount);
+    uint32_t *entries = (uint32_t *)(st.buf + o_entries);
+    J *partials = (J *)(st.buf + o_partials), *buckets = (J *)(st.buf + o_buckets), *segs = (J *)(st.buf + o_segs);
     MCK(cudaMemsetAsync(counts, 0, nb * 4, s));
-    k_msm_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, sb, nbits, c, nwin, counts);
-    k_msm_scan<<<1, 1024, 0, s>>>(counts, nb, offsets, cursor);
-    k_msm_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, sb, nbits, c, nwin, cursor, entries);
-    k_msm_bucket<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(d_points, offsets, entries, nb, buckets);
+    MCK(cudaMemsetAsync(bigcount, 0, 4, s));
+    int nl = 0;
+    k_msm_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, sstride, n, sb, nbits, c, nwin, counts);
+    k_msm_scan<<<1, 1024, 0, s>>>(counts, nb, ch, offsets, cursor, toff);
+    k_msm_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, sstride, n, sb, nbits, c, nwin, cursor, entries);
+    k_msm_task<F><<<(unsigned)((tmax + 127) / 128), 128, 0, s>>>(d_points, pstride, offsets, toff, entries, nb, ch, partials);
+    k_msm_combine<F><<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(partials, toff, nb, buckets, biglist, bigcount);
+    k_msm_combine_big<F><<<64, 128, 0, s>>>(partials, toff, biglist, bigcount, buckets);
     size_t nt = (size_t)nwin * nseg;
-    k_msm_segment<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(buckets, c, nwin, segs);
+    k_msm_segment<F><<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(buckets, c, nwin, (uint32_t)L, segs);
+    nl += 7;
     for (size_t m = nseg; m > 1;) {
         size_t half = (m + 1) / 2;
-        k_g1_tree_rows<<<(unsigned)(((size_t)nwin * half + 127) / 128), 128, 0, s>>>(segs, nwin, nseg, m, half);
+        k_tree_rows<F><<<(unsigned)(((size_t)nwin * half + 127) / 128), 128, 0, s>>>(segs, nwin, nseg, m, half);
+        nl++;
         m = half;
     }
-    k_msm_horner<<<1, 32, 0, s>>>(segs, nseg, nwin, c, d_out);
+    k_msm_horner<F><<<1, 32, 0, s>>>(segs, nseg, nwin, c, d_out_jac, d_out_aff);
+    nl++;
     MCK(cudaGetLastError());
-    MCK(cudaMemcpyAsync(h_out, d_out, 96, cudaMemcpyDeviceToHost, s));
-    MCK(cudaStreamSynchronize(s));
 #undef MCK
+    if (launches) *launches += nl;
     return 0;
 }
 

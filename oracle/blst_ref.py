@@ -114,6 +114,14 @@ def msm_g1(points96, scalars32, nbits=255):
     return bytes(out)
 
 
+def msm_g2(points192, scalars, nbits=255):
+    """blst_p2s_mult_pippenger + to_affine on n x 192-byte affine points, scalars n x ceil(nbits/8) bytes LE."""
+    n = len(points192) // 192
+    out = _out(192)
+    ref.ref_msm_g2(_buf(points192), _buf(scalars), C.c_size_t(n), C.c_size_t(nbits), out)
+    return bytes(out)
+
+
 def time_msm_g1(points96, scalars32, nbits=255, reps=1):
     n = len(points96) // 96
     return float(ref.ref_time_msm_g1(_buf(points96), _buf(scalars32), C.c_size_t(n), C.c_size_t(nbits), C.c_int(reps)))

@@ -340,6 +340,20 @@ int ref_msm_g1(const uint8_t *pts, const uint8_t *scalars, size_t n, size_t nbit
     return 1;
 }
 
+/* G2 MSM: blst_p2s_mult_pippenger (multi_scalar.c:442-446), the shape combine() uses with nbits = 64
+ * (blst_min_pubkey_sig_core.nim:637-644) */
+int ref_msm_g2(const uint8_t *pts, const uint8_t *scalars, size_t n, size_t nbits, uint8_t out[192]) {
+    if (n == 0) { memset(out, 0, 192); return 0; }
+    const blst_p2_affine *pp[2] = { (const blst_p2_affine *)pts, NULL };
+    const uint8_t *ss[2] = { scalars, NULL };
+    void *scratch = malloc(blst_p2s_mult_pippenger_scratch_sizeof(n));
+    blst_p2 r;
+    blst_p2s_mult_pippenger(&r, pp, n, ss, nbits, scratch);
+    blst_p2_to_affine((blst_p2_affine *)out, &r);
+    free(scratch);
+    return 1;
+}
+
 double ref_time_msm_g1(const uint8_t *pts, const uint8_t *scalars, size_t n, size_t nbits, int reps) {
     const blst_p1_affine *pp[2] = { (const blst_p1_affine *)pts, NULL };
     const uint8_t *ss[2] = { scalars, NULL };

@@ -54,3 +54,33 @@ def test_msm_device_inputs_match_oracle(cache, br):
     out = (C.c_uint8 * 96)()
     assert L.blsgpu_msm_g1_dev(cache.handle, C.c_void_p(dp.data_ptr()), C.c_void_p(ds.data_ptr()), n, 255, out) == 1
     assert bytes(out) == br.msm_g1(dp.cpu().numpy().tobytes(), ds.cpu().numpy().tobytes(), 255)
+
+
+def _g2_points(br, n, seed=3):
+    """n affine G2 points: the signatures of deterministic signature sets (192 B each)."""
+    sets = br.make_sets(seed, n)
+    return b"".join(sets[i * 320 + 128:(i + 1) * 320] for i in range(n))
+
+
+@pytest.mark.parametrize("n,nbits", [(1, 64), (2, 64), (33, 64), (257, 64), (3000, 64), (500, 255), (129, 128)])
+def test_msm_g2(cache, br, n, nbits):
+    """G2 MSM vs blst_p2s_mult_pippenger; nbits=64 is the signature half of MultiSignatureSet.combine
+    (blst_min_pubkey_sig_core.nim:637-644)."""
+    import nim_blscurve_b200 as bg
+    pts = _g2_points(br, n)
+    rng = random.Random(n * 1000 + nbits)
+    sb = (nbits + 7) // 8
+    sc = b"".join(rng.getrandbits(nbits).to_bytes(sb, "little") for _ in range(n))
+    assert bg.msmG2(cache, pts, sc, nbits) == br.msm_g2(pts, sc, nbits)
+
+
+def test_msm_skewed_scalars(cache, br):
+    """Every scalar equal: each window has ONE full bucket (the task split + warp-cooperative combine path)."""
+    import nim_blscurve_b200 as bg
+    n = 5000
+    pts, _ = br.msm_points(21, n)
+    sc = (0x1234567890abcdef1122334455667788).to_bytes(32, "little") * n
+    assert bg.msmG1(cache, pts, sc, 255) == br.msm_g1(pts, sc, 255)
+    g2 = _g2_points(br, 700)
+    sc2 = (0xfedcba9876543210).to_bytes(8, "little") * 700
+    assert bg.msmG2(cache, g2, sc2, 64) == br.msm_g2(g2, sc2, 64)
