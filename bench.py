@@ -31,7 +31,9 @@ CHUNKS_PER_GPU = 1024          # reference chunk count (tp.numThreads) used for 
 W_SET = 12725                  # Fp-mul per set of the reference algorithm
 W_BATCH = 14673                # per batch finalisation
 IMAD_PER_FPMUL = 300
-STAGE_FPMUL = {"hash_to_g2": 4919, "g1_mul64": 800, "pairs_affine": 23, "g2_mul64": 2028, "miller_loop": 4955}
+# reference-algorithm Fp-mul per set of each stage: A3, A5 (G1), A4, and A7 split into its line
+# evaluations (63 x (25+4) + 5 x (35+4)) and its accumulation (68 x 39 + shared squarings)
+STAGE_FPMUL = {"hash_to_g2": 4919, "g1_mul64": 800, "pairs_affine": 23, "miller_lines": 2022, "miller_acc": 2933}
 
 
 def clocks_sampler(stop, out, gpu_index):

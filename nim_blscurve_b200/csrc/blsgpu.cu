@@ -7,10 +7,12 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <map>
 #include <vector>
 #include "../../include/blsgpu.h"
 #include "kernels.cuh"
 #include "msm.cuh"
+#include "fpprog.hpp"
 
 using namespace bls;
 
@@ -38,7 +40,7 @@ struct blsgpu_ctx {
     uint32_t *d_lines = nullptr;  // 68 x 72 words x lines_stride
     size_t lines_cap = 0;         // pairs per tile
     fp12 *d_partials = nullptr;   // 64 slots
-    uint8_t *d_gt = nullptr;      // 576
+    uint8_t *d_gtb = nullptr;     // 576 canonical GT bytes
     int *d_flags = nullptr;       // [0] pk infinity, [1] is_one
     void *d_misc = nullptr;       // scratch for aggregate / hash API
     size_t misc_bytes = 0;
@@ -49,6 +51,12 @@ struct blsgpu_ctx {
     float stage_ms[ST_COUNT];
     int launches = 0;
     msm_state msm;
+    // warp-cooperative tail programs (fpprog.hpp), compiled on first use and kept on the device
+    struct dev_prog { uint32_t *d = nullptr; int nslots = 0, nrounds = 0; };
+    std::map<int, dev_prog> combine_progs, final_progs;      // keyed by segment count / partial count
+    fp *d_consts = nullptr;                                  // Frobenius coefficients (fpprog::CONST_*)
+    fp12 *d_gt = nullptr;                                    // final exponentiation result, Montgomery form
+    bool serial_tail = false;
     std::string err;
 };
 
@@ -83,8 +91,10 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_r); cudaFree(ctx->d_H); cudaFree(ctx->d_Pj); cudaFree(ctx->d_Q);
-    cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gt);
-    cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines);
+    cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gtb);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_consts); cudaFree(ctx->d_gt);
+    for (auto &kv : ctx->combine_progs) cudaFree(kv.second.d);
+    for (auto &kv : ctx->final_progs) cudaFree(kv.second.d); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i <= ST_COUNT; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
@@ -127,10 +137,17 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     ALLOC(ctx->d_F, ctx->f_cap * sizeof(fp12));
     ALLOC(ctx->d_seg, 64 * sizeof(fp12));
     ALLOC(ctx->d_partials, 64 * sizeof(fp12));
-    ALLOC(ctx->d_gt, 576);
+    ALLOC(ctx->d_gtb, 576);
+    ALLOC(ctx->d_gt, sizeof(fp12));
+    ALLOC(ctx->d_consts, fpprog::CONST_COUNT * sizeof(fp));
     ALLOC(ctx->d_flags, 4 * sizeof(int));
 #undef ALLOC
     if ((e = cudaMallocHost((void **)&ctx->h_pinned, 4096)) != cudaSuccess) return bad("cudaMallocHost", e);
+    if ((e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB1, FROB1, sizeof(FROB1), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
+        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB2, FROB2, sizeof(FROB2), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
+        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB3, FROB3, sizeof(FROB3), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess)
+        return bad("cudaMemcpyFromSymbol(FROB)", e);
+    ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
     for (int i = 0; i <= ST_COUNT; i++) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
         ctx->ev_valid[i] = true;
@@ -183,6 +200,41 @@ static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size
     k_rlc_scalars<<<nblk(nb, 64), 64, 0, s>>>(words_of(srb), total_n, chunks, first, n, ctx->d_r);
     ctx->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+// Compile (once) and fetch a tail program; kind 0 = combine over `key` segments, 1 = final exponentiation of `key` partials
+static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &out) {
+    std::map<int, blsgpu_ctx::dev_prog> &cache = kind == 0 ? ctx->combine_progs : ctx->final_progs;
+    auto it = cache.find(key);
+    if (it != cache.end()) { out = it->second; return 0; }
+    fpprog::Program P;
+    if (kind == 0) {
+        int len[64];
+        for (int j = 0; j < key; j++) len[j] = ml_seg_hi(j, key) - ml_seg_lo(j, key) + 1;
+        P = fpprog::build_combine(key, len);
+    } else {
+        P = fpprog::build_final(key);
+    }
+    if (!P.ok) return fail(ctx, BLSGPU_ERR_ARG, "tail program does not fit the slot file");
+    blsgpu_ctx::dev_prog dp;
+    dp.nslots = P.nslots;
+    dp.nrounds = P.nrounds;
+    CK(cudaMalloc((void **)&dp.d, P.words.size() * 4));
+    CK(cudaMemcpy(dp.d, P.words.data(), P.words.size() * 4, cudaMemcpyHostToDevice));
+    cache[key] = dp;
+    out = dp;
+    return 0;
+}
+
+static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp *in0, fp *out0) {
+    size_t smem = (size_t)p.nslots * sizeof(fp);
+    if (smem > 48 * 1024) {
+        static bool raised = false;
+        if (!raised) { CK(cudaFuncSetAttribute(k_fp_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); raised = true; }
+    }
+    k_fp_program<<<1, 32, smem, ctx->stream>>>(p.d, in0, nullptr, ctx->d_consts, out0);
+    ctx->launches++;
     return 0;
 }
 
@@ -268,8 +320,17 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     MARK(ST_GTPROD);
     k_fp12_rows<<<nseg, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_seg);
     MARK(ST_PARTIAL);
-    k_combine<<<1, 32, 0, s>>>(ctx->d_seg, nseg, ctx->d_partials + slot);
-    ctx->launches += 2;
+    ctx->launches++;
+    if (ctx->serial_tail) {
+        k_combine<<<1, 32, 0, s>>>(ctx->d_seg, nseg, ctx->d_partials + slot);
+        ctx->launches++;
+    } else {
+        blsgpu_ctx::dev_prog cp;
+        rc = get_prog(ctx, 0, nseg, cp);
+        if (rc) return rc;
+        rc = launch_prog(ctx, cp, (const fp *)ctx->d_seg, (fp *)(ctx->d_partials + slot));
+        if (rc) return rc;
+    }
     MARK(ST_FINAL);
     CK(cudaGetLastError());
     return 0;
@@ -278,10 +339,21 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
 static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_inf, const fp12 *d_partials = nullptr,
                      const int *d_rank_flags = nullptr) {
     cudaStream_t s = ctx->stream;
-    k_final<<<1, 32, 0, s>>>(d_partials ? d_partials : ctx->d_partials, count, d_rank_flags, ctx->d_gt, ctx->d_flags + 1);
-    ctx->launches++;
+    const fp12 *parts = d_partials ? d_partials : ctx->d_partials;
+    if (ctx->serial_tail) {
+        k_final<<<1, 32, 0, s>>>(parts, count, d_rank_flags, ctx->d_gtb, ctx->d_flags + 1);
+        ctx->launches++;
+    } else {
+        blsgpu_ctx::dev_prog fpg;
+        int rc = get_prog(ctx, 1, count, fpg);
+        if (rc) return rc;
+        rc = launch_prog(ctx, fpg, (const fp *)parts, (fp *)ctx->d_gt);
+        if (rc) return rc;
+        k_final_out<<<1, 32, 0, s>>>(ctx->d_gt, count, d_rank_flags, ctx->d_gtb, ctx->d_flags + 1);
+        ctx->launches++;
+    }
     CK(cudaEventRecord(ctx->ev[ST_COUNT], s));
-    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_gt, 576, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_gtb, 576, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_pinned + 576, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     int flags[4];

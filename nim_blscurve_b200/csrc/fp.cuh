@@ -17,10 +17,12 @@
 
 #ifdef __CUDACC__
 #define BLS_FN __device__ __forceinline__
+#define BLS_HD __host__ __device__ __forceinline__
 #define BLS_NOINLINE __device__ __noinline__
 #define BLS_TABLE __device__ __constant__ const
 #else
 #define BLS_FN static inline
+#define BLS_HD static inline
 #define BLS_NOINLINE static
 #define BLS_TABLE static const
 #endif

@@ -1,0 +1,352 @@
+// fpprog.hpp — host-side compiler for the warp-cooperative tail of the batch verifier.
+//
+// The per-batch tail (stitching the Miller-loop segments: 63 Fp12 squarings; the product of the rank partials; the
+// final exponentiation of vendor/blst/src/pairing.c:371-404) is a few thousand Fp operations with a long dependency
+// chain and plenty of instruction-level parallelism (an Fp12 product is 54 independent Fp multiplications).  One
+// thread wastes that; 32 lanes can share it.  This header TRACES the tower formulas into a dataflow graph of
+// Fp operations (mul / add / sub), list-schedules the graph into rounds of at most 32 independent operations of
+// one kind, assigns shared-memory slots by liveness, and serialises the result.  The device interpreter
+// (k_fp_program in kernels.cuh) executes one round per step: lane l performs operation l of the round on
+// 48-byte slots in shared memory.
+//
+// Pure C++ (no CUDA): included by blsgpu.cu to build the programs at context creation and by tests/hostsim to
+// execute them on the CPU against the straight-line formulas of tower.cuh / pairing.cuh.
+#pragma once
+#include <stdint.h>
+#include <algorithm>
+#include <queue>
+#include <utility>
+#include <vector>
+
+namespace fpprog {
+
+enum { OP_NOP = 0, OP_MUL = 1, OP_ADD = 2, OP_SUB = 3, OP_LEAF = 4 };
+enum { LANES = 32, MAX_SLOTS = 1024, ROUND_WORDS = LANES };
+// buffer ids of the I/O tables
+enum { BUF_IN0 = 0, BUF_IN1 = 1, BUF_CONST = 2, BUF_OUT0 = 3 };
+// fp indices inside the constant pool (BUF_CONST): Frobenius coefficients as fp2 = 2 fp each
+enum { CONST_FROB1 = 0, CONST_FROB2 = 10, CONST_FROB3 = 20, CONST_COUNT = 30 };
+
+struct Node { uint8_t op; int32_t a, b; };
+struct IoRef { int32_t node, buf, idx; };
+
+struct Builder {
+    std::vector<Node> nodes;
+    std::vector<IoRef> inputs, outputs;
+    Builder() { nodes.push_back({OP_LEAF, -1, -1}); }            // node 0 = the constant zero (slot 0)
+    int leaf(int buf, int idx) {
+        for (const IoRef &r : inputs) if (r.buf == buf && r.idx == idx) return r.node;
+        nodes.push_back({OP_LEAF, -1, -1});
+        inputs.push_back({(int32_t)nodes.size() - 1, buf, idx});
+        return (int)nodes.size() - 1;
+    }
+    int emit(int op, int a, int b) {
+        if ((op == OP_ADD || op == OP_SUB) && b == 0) return a;
+        if (op == OP_ADD && a == 0) return b;
+        if (op == OP_MUL && (a == 0 || b == 0)) return 0;
+        nodes.push_back({(uint8_t)op, a, b});
+        return (int)nodes.size() - 1;
+    }
+    void output(int node, int buf, int idx) { outputs.push_back({node, buf, idx}); }
+};
+
+static thread_local Builder *g_b = nullptr;
+
+// ---- traced field elements -----------------------------------------------------------------------
+struct V { int id; };
+inline V operator+(V a, V b) { return {g_b->emit(OP_ADD, a.id, b.id)}; }
+inline V operator-(V a, V b) { return {g_b->emit(OP_SUB, a.id, b.id)}; }
+inline V operator*(V a, V b) { return {g_b->emit(OP_MUL, a.id, b.id)}; }
+inline V vzero() { return {0}; }
+inline V vneg(V a) { return vzero() - a; }
+
+struct V2 { V c0, c1; };
+inline V2 operator+(V2 a, V2 b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
+inline V2 operator-(V2 a, V2 b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
+inline V2 neg(V2 a) { return {vneg(a.c0), vneg(a.c1)}; }
+inline V2 dbl(V2 a) { return a + a; }
+inline V2 conj(V2 a) { return {a.c0, vneg(a.c1)}; }
+inline V2 mul_xi(V2 a) { return {a.c0 - a.c1, a.c0 + a.c1}; }          // * (1+u)
+inline V2 operator*(V2 a, V2 b) {                                       // Karatsuba, as fp2_mul
+    V t2 = (a.c0 + a.c1) * (b.c0 + b.c1), t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
+    return {t0 - t1, t2 - t0 - t1};
+}
+inline V2 sqr(V2 a) {                                                   // as fp2_sqr
+    V t = a.c0 * a.c1;
+    return {(a.c0 + a.c1) * (a.c0 - a.c1), t + t};
+}
+inline V2 mul_fp(V2 a, V k) { return {a.c0 * k, a.c1 * k}; }
+inline V2 zero2() { return {vzero(), vzero()}; }
+
+struct V6 { V2 c0, c1, c2; };
+inline V6 operator+(V6 a, V6 b) { return {a.c0 + b.c0, a.c1 + b.c1, a.c2 + b.c2}; }
+inline V6 operator-(V6 a, V6 b) { return {a.c0 - b.c0, a.c1 - b.c1, a.c2 - b.c2}; }
+inline V6 neg(V6 a) { return {neg(a.c0), neg(a.c1), neg(a.c2)}; }
+inline V6 dbl(V6 a) { return a + a; }
+inline V6 mul_v(V6 a) { return {mul_xi(a.c2), a.c0, a.c1}; }
+inline V6 operator*(V6 a, V6 b) {                                       // as fp6_mul
+    V2 t0 = a.c0 * b.c0, t1 = a.c1 * b.c1, t2 = a.c2 * b.c2;
+    V2 c0 = mul_xi((a.c1 + a.c2) * (b.c1 + b.c2) - t1 - t2) + t0;
+    V2 c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - t0 - t1 + mul_xi(t2);
+    V2 c2 = (a.c0 + a.c2) * (b.c0 + b.c2) - t0 - t2 + t1;
+    return {c0, c1, c2};
+}
+
+struct V12 { V6 c0, c1; };
+inline V12 operator*(V12 a, V12 b) {                                    // as fp12_mul
+    V6 t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
+    V6 s = (a.c0 + a.c1) * (b.c0 + b.c1) - t0 - t1;
+    return {t0 + mul_v(t1), s};
+}
+inline V12 sqr(V12 a) {                                                 // complex squaring, as fp12_sqr
+    V6 t = a.c0 * a.c1;
+    V6 s = (a.c0 + a.c1) * (mul_v(a.c1) + a.c0) - t - mul_v(t);
+    return {s, dbl(t)};
+}
+inline V12 conj(V12 a) { return {a.c0, neg(a.c1)}; }
+
+// p - 2, little-endian 64-bit words (p: vendor/blst/src/consts.c:10-14)
+static const uint64_t P_MINUS_2[6] = {0xb9feffffffffaaa9ull, 0x1eabfffeb153ffffull, 0x6730d2a0f6b0f624ull,
+                                      0x64774b84f38512bfull, 0x4b1ba7b6434bacd7ull, 0x1a0111ea397fe69aull};
+
+// 1/a = a^(p-2), fixed 4-bit windows (0 -> 0)
+inline V inv(V a) {
+    V tbl[16];
+    tbl[1] = a;
+    for (int i = 2; i < 16; i++) tbl[i] = tbl[i - 1] * a;
+    V acc = {0};
+    bool started = false;
+    for (int nib = 95; nib >= 0; nib--) {
+        int d = (int)((P_MINUS_2[nib / 16] >> (4 * (nib % 16))) & 15);
+        if (started) for (int k = 0; k < 4; k++) acc = acc * acc;
+        if (d) {
+            if (started) acc = acc * tbl[d]; else { acc = tbl[d]; started = true; }
+        }
+    }
+    return acc;
+}
+inline V2 inv(V2 a) {
+    V ni = inv(a.c0 * a.c0 + a.c1 * a.c1);
+    return {a.c0 * ni, vneg(a.c1 * ni)};
+}
+inline V6 inv(V6 a) {                                                   // as fp6_inv
+    V2 c0 = sqr(a.c0) - mul_xi(a.c1 * a.c2);
+    V2 c1 = mul_xi(sqr(a.c2)) - a.c0 * a.c1;
+    V2 c2 = sqr(a.c1) - a.c0 * a.c2;
+    V2 t = inv(mul_xi(a.c2 * c1 + a.c1 * c2) + a.c0 * c0);
+    return {c0 * t, c1 * t, c2 * t};
+}
+inline V12 inv(V12 a) {                                                 // as fp12_inv
+    V6 t = inv(a.c0 * a.c0 - mul_v(a.c1 * a.c1));
+    return {a.c0 * t, neg(a.c1 * t)};
+}
+
+inline V2 const2(int base, int k) { return {{g_b->leaf(BUF_CONST, base + 2 * k)}, {g_b->leaf(BUF_CONST, base + 2 * k + 1)}}; }
+
+// a^(p^n), n = 1..3 (as fp12_frob): coefficient of v^i w^j times FROBn[2i+j-1], conjugated first for odd n
+inline V12 frob(V12 a, int n) {
+    const int base = n == 1 ? CONST_FROB1 : (n == 2 ? CONST_FROB2 : CONST_FROB3);
+    V2 *src[6] = {&a.c0.c0, &a.c0.c1, &a.c0.c2, &a.c1.c0, &a.c1.c1, &a.c1.c2};
+    V2 dst[6];
+    for (int j = 0; j < 2; j++)
+        for (int i = 0; i < 3; i++) {
+            V2 c = *src[3 * j + i];
+            if (n & 1) c = conj(c);
+            int k = 2 * i + j;
+            if (k) c = c * const2(base, k - 1);
+            dst[3 * j + i] = c;
+        }
+    return {{dst[0], dst[1], dst[2]}, {dst[3], dst[4], dst[5]}};
+}
+
+inline void fp4_sqr(V2 &t0, V2 &t1, V2 a, V2 b) {
+    V2 a2 = sqr(a), b2 = sqr(b);
+    t1 = sqr(a + b) - a2 - b2;
+    t0 = a2 + mul_xi(b2);
+}
+inline V12 cyc_sqr(V12 a) {                                             // Granger-Scott, as fp12_cyc_sqr
+    V2 z0 = a.c0.c0, z4 = a.c0.c1, z3 = a.c0.c2, z2 = a.c1.c0, z1 = a.c1.c1, z5 = a.c1.c2, t0, t1, t2, t3;
+    fp4_sqr(t0, t1, z0, z1);
+    z0 = dbl(t0 - z0) + t0;
+    z1 = dbl(t1 + z1) + t1;
+    fp4_sqr(t0, t1, z2, z3);
+    fp4_sqr(t2, t3, z4, z5);
+    z4 = dbl(t0 - z4) + t0;
+    z5 = dbl(t1 + z5) + t1;
+    t3 = mul_xi(t3);
+    z2 = dbl(t3 + z2) + t3;
+    z3 = dbl(t2 - z3) + t2;
+    return {{z0, z4, z3}, {z2, z1, z5}};
+}
+
+static const uint64_t Z_ABS = 0xd201000000010000ull;
+inline V12 cyc_exp_z(V12 a) {
+    V12 acc = a;
+    for (int i = 62; i >= 0; i--) {
+        acc = cyc_sqr(acc);
+        if ((Z_ABS >> i) & 1) acc = acc * a;
+    }
+    return conj(acc);
+}
+
+// f^(3 (p^12-1)/r), the exponent of pairing.c:371-404 (same chain as final_exp in pairing.cuh)
+inline V12 final_exp(V12 f) {
+    V12 t = conj(f) * inv(f);
+    t = frob(t, 2) * t;
+    V12 a = cyc_exp_z(t) * conj(t);
+    a = cyc_exp_z(a) * conj(a);
+    V12 b = cyc_exp_z(a) * frob(a, 1);
+    V12 c = cyc_exp_z(cyc_exp_z(b)) * frob(b, 2) * conj(b);
+    V12 d = cyc_sqr(t) * t;
+    return c * d;
+}
+
+inline V12 load12(int buf, int base) {
+    V2 c[6];
+    for (int k = 0; k < 6; k++) c[k] = {{g_b->leaf(buf, base + 2 * k)}, {g_b->leaf(buf, base + 2 * k + 1)}};
+    return {{c[0], c[1], c[2]}, {c[3], c[4], c[5]}};
+}
+inline void store12(V12 a, int buf, int base) {
+    V2 c[6] = {a.c0.c0, a.c0.c1, a.c0.c2, a.c1.c0, a.c1.c1, a.c1.c2};
+    for (int k = 0; k < 6; k++) { g_b->output(c[k].c0.id, buf, base + 2 * k); g_b->output(c[k].c1.id, buf, base + 2 * k + 1); }
+}
+
+// ---- scheduling + slot allocation ------------------------------------------------------------------
+struct Program {
+    std::vector<uint32_t> words;      // [nrounds, nslots, n_in, n_out] + in table + out table + rounds
+    int nrounds = 0, nmul_rounds = 0, nslots = 0, nops = 0;
+    bool ok = false;
+};
+
+inline uint32_t enc(int op, int d, int a, int b) { return ((uint32_t)op << 30) | ((uint32_t)d << 20) | ((uint32_t)a << 10) | (uint32_t)b; }
+
+inline Program compile(const Builder &B, int slack = 40) {
+    const int N = (int)B.nodes.size();
+    Program P;
+    std::vector<char> live(N, 0);
+    for (const IoRef &o : B.outputs) live[o.node] = 1;
+    for (int n = N - 1; n >= 0; n--)
+        if (live[n] && B.nodes[n].op != OP_LEAF) { live[B.nodes[n].a] = 1; live[B.nodes[n].b] = 1; }
+    // priority: longest weighted path to an output
+    std::vector<int> height(N, 0);
+    for (int n = N - 1; n >= 0; n--) {
+        if (!live[n] || B.nodes[n].op == OP_LEAF) continue;
+        int h = height[n] + (B.nodes[n].op == OP_MUL ? 10 : 1);
+        height[B.nodes[n].a] = std::max(height[B.nodes[n].a], h);
+        height[B.nodes[n].b] = std::max(height[B.nodes[n].b], h);
+    }
+    std::vector<std::vector<int>> users(N);
+    std::vector<int> pending(N, 0), round_of(N, -1);
+    typedef std::pair<int, int> PQE;       // (height, -node)
+    std::priority_queue<PQE> q_mul, q_lin;
+    auto push_ready = [&](int n) { (B.nodes[n].op == OP_MUL ? q_mul : q_lin).push({height[n], -n}); };
+    for (int n = 0; n < N; n++) {
+        if (!live[n] || B.nodes[n].op == OP_LEAF) continue;
+        int a = B.nodes[n].a, b = B.nodes[n].b, cnt = 0;
+        if (B.nodes[a].op != OP_LEAF) { users[a].push_back(n); cnt++; }
+        if (b != a && B.nodes[b].op != OP_LEAF) { users[b].push_back(n); cnt++; }
+        pending[n] = cnt;
+        if (cnt == 0) push_ready(n);
+    }
+    // Rounds: operations far off the critical path (height more than `slack` below the most urgent ready one) wait,
+    // which keeps the number of live values — shared-memory slots — bounded; cheap add/sub rounds go first so
+    // that the expensive multiplication rounds are as full as possible.
+    std::vector<std::vector<int>> rounds;
+    std::vector<char> round_is_mul;
+    while (!q_mul.empty() || !q_lin.empty()) {
+        int hmax = std::max(q_mul.empty() ? -1 : q_mul.top().first, q_lin.empty() ? -1 : q_lin.top().first);
+        bool is_mul = q_lin.empty() || q_lin.top().first < hmax - slack;
+        std::priority_queue<PQE> &q = is_mul ? q_mul : q_lin;
+        std::vector<int> ops;
+        while (!q.empty() && (int)ops.size() < LANES && q.top().first >= hmax - slack) { ops.push_back(-q.top().second); q.pop(); }
+        const int r = (int)rounds.size();
+        for (int n : ops) round_of[n] = r;
+        for (int n : ops)
+            for (int u : users[n]) if (--pending[u] == 0) push_ready(u);
+        rounds.push_back(ops);
+        round_is_mul.push_back(is_mul);
+    }
+    // liveness: last round in which each value is read
+    const int NR = (int)rounds.size();
+    std::vector<int> last_use(N, -1);
+    for (int r = 0; r < NR; r++)
+        for (int n : rounds[r]) { last_use[B.nodes[n].a] = r; last_use[B.nodes[n].b] = r; }
+    for (const IoRef &o : B.outputs) last_use[o.node] = NR + 1;
+    last_use[0] = NR + 1;
+    std::vector<int> slot(N, -1);
+    slot[0] = 0;
+    std::priority_queue<int, std::vector<int>, std::greater<int>> free_slots;
+    int next_slot = 1;
+    auto alloc = [&]() { if (!free_slots.empty()) { int s = free_slots.top(); free_slots.pop(); return s; } return next_slot++; };
+    std::vector<std::vector<int>> expire(NR + 2);
+    for (const IoRef &in : B.inputs)
+        if (live[in.node]) {
+            slot[in.node] = alloc();
+            if (last_use[in.node] >= 0 && last_use[in.node] <= NR) expire[last_use[in.node]].push_back(in.node);
+        }
+    for (int r = 0; r < NR; r++) {
+        for (int n : rounds[r]) {
+            slot[n] = alloc();
+            if (last_use[n] <= NR) expire[last_use[n] < r ? r : last_use[n]].push_back(n);
+        }
+        for (int n : expire[r]) free_slots.push(slot[n]);
+    }
+    P.nslots = next_slot;
+    if (next_slot > MAX_SLOTS) return P;
+    // serialise
+    std::vector<IoRef> ins;
+    for (const IoRef &in : B.inputs) if (live[in.node]) ins.push_back(in);
+    P.words = {(uint32_t)NR, (uint32_t)P.nslots, (uint32_t)ins.size(), (uint32_t)B.outputs.size()};
+    for (const IoRef &in : ins) { P.words.push_back((uint32_t)slot[in.node]); P.words.push_back(((uint32_t)in.buf << 24) | (uint32_t)in.idx); }
+    for (const IoRef &o : B.outputs) { P.words.push_back((uint32_t)slot[o.node]); P.words.push_back(((uint32_t)o.buf << 24) | (uint32_t)o.idx); }
+    for (int r = 0; r < NR; r++) {
+        for (int l = 0; l < LANES; l++) {
+            if (l < (int)rounds[r].size()) {
+                int n = rounds[r][l];
+                P.words.push_back(enc(B.nodes[n].op, slot[n], slot[B.nodes[n].a], slot[B.nodes[n].b]));
+                P.nops++;
+            } else {
+                P.words.push_back(0u);
+            }
+        }
+        P.nmul_rounds += round_is_mul[r] ? 1 : 0;
+    }
+    P.nrounds = NR;
+    P.ok = true;
+    return P;
+}
+
+// ---- the three tail programs -------------------------------------------------------------------------
+// Horner over nseg Miller-loop segment products (IN0: nseg x 12 fp) -> rank partial (OUT0: 12 fp); mirrors
+// miller_combine() in pairing.cuh.  seg_len[j] = number of loop iterations of segment j.
+inline Program build_combine(int nseg, const int *seg_len) {
+    Builder b;
+    g_b = &b;
+    V12 acc = load12(BUF_IN0, 0);
+    for (int j = 1; j < nseg; j++) {
+        for (int t = 0; t < seg_len[j]; t++) acc = sqr(acc);
+        acc = acc * load12(BUF_IN0, 12 * j);
+    }
+    store12(conj(acc), BUF_OUT0, 0);
+    g_b = nullptr;
+    return compile(b);
+}
+
+// product of `count` partials (IN0: count x 12 fp) followed by the final exponentiation -> OUT0: 12 fp
+inline Program build_final(int count) {
+    Builder b;
+    g_b = &b;
+    std::vector<V12> v;
+    for (int i = 0; i < count; i++) v.push_back(load12(BUF_IN0, 12 * i));
+    while (v.size() > 1) {                                  // balanced product tree
+        std::vector<V12> w;
+        for (size_t i = 0; i + 1 < v.size(); i += 2) w.push_back(v[i] * v[i + 1]);
+        if (v.size() & 1) w.push_back(v.back());
+        v.swap(w);
+    }
+    store12(final_exp(v[0]), BUF_OUT0, 0);
+    g_b = nullptr;
+    return compile(b);
+}
+
+}  // namespace fpprog

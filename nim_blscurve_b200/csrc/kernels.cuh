@@ -281,7 +281,69 @@ __global__ void k_copy_flag(const int *src, int *dst) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *dst = *src;
 }
 
-// prod partials -> final exponentiation -> (== 1), canonical GT bytes
+// ---- warp-cooperative tail: interpreter for the Fp dataflow programs compiled by fpprog.hpp ----
+// One warp; field elements live in 48-byte shared-memory slots (slot 0 = zero).  Every round holds at most 32
+// independent operations of one kind (32 words per round, word = op:2 | dst:10 | a:10 | b:10, 0 = idle); lane l executes
+// operation l.  A slot written
+// in round r is never read in round r (fpprog.hpp frees slots only after their last reading round), so one warp
+// barrier per round orders everything.
+__global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst, fp *out0) {
+    extern __shared__ uint4 sm4[];
+    fp *slots = (fp *)sm4;
+    const int lane = threadIdx.x;
+    const uint32_t nr = prog[0], nin = prog[2], nout = prog[3];
+    if (lane == 0) fp_set_zero(slots[0]);
+    for (uint32_t e = lane; e < nin; e += 32) {
+        uint32_t sl = prog[4 + 2 * e], ref = prog[5 + 2 * e], buf = ref >> 24, idx = ref & 0xffffffu;
+        const fp *src = buf == 0 ? in0 : (buf == 1 ? in1 : cst);
+        slots[sl] = src[idx];
+    }
+    __syncwarp();
+    // operation words are prefetched four rounds ahead so that their global-memory latency overlaps the arithmetic
+    const uint32_t *rp = prog + 4 + 2 * (nin + nout) + lane;
+    uint32_t wq[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) wq[k] = (uint32_t)k < nr ? rp[32 * k] : 0u;
+    for (uint32_t r = 0; r < nr; r += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t w = wq[k];
+            wq[k] = r + k + 4 < nr ? rp[32 * (r + k + 4)] : 0u;
+            if (w) {
+                fp x = slots[(w >> 10) & 1023], y = slots[w & 1023], t;
+                const uint32_t opc = w >> 30;
+                if (opc == 1) fp_mul(t, x, y);
+                else if (opc == 2) fp_add(t, x, y);
+                else fp_sub(t, x, y);
+                slots[(w >> 20) & 1023] = t;
+            }
+            __syncwarp();
+        }
+    }
+    const uint32_t *op = prog + 4 + 2 * nin;
+    for (uint32_t e = lane; e < nout; e += 32) out0[op[2 * e + 1] & 0xffffffu] = slots[op[2 * e]];
+}
+
+// verdict and canonical GT bytes of the final exponentiation result (fp12_tower.c:773-786): 12 lanes, one Fp each
+__global__ void k_final_out(const fp12 *gt, int count, const int *flags, uint8_t *gt_bytes, int *is_one) {
+    const int t = threadIdx.x;
+    if (blockIdx.x != 0 || t >= 12) return;
+    if (t == 0) {
+        int bad = 0;
+        if (flags) for (int i = 0; i < count; i++) bad |= flags[i];
+        is_one[1] = bad;
+        is_one[0] = fp12_is_one(*gt) ? 1 : 0;
+    }
+    // output order: for i in 0..2, j in 0..1: a[j][i].re || a[j][i].im  -> Fp number t = 4i + 2j + k reads c[3j+i].k
+    const int i = t >> 2, j = (t >> 1) & 1, k = t & 1;
+    const fp2 *c = &gt->c0.c0;
+    fp v;
+    fp_from_mont(v, k ? c[3 * j + i].c1 : c[3 * j + i].c0);
+    uint8_t *out = gt_bytes + 48 * t;
+    for (int b = 0; b < 48; b++) out[b] = (uint8_t)(v.l[(47 - b) >> 2] >> (8 * ((47 - b) & 3)));
+}
+
+// single-thread reference of the same tail (kept for BLSGPU_SERIAL_TAIL=1 cross-checks)
 __global__ void k_final(const fp12 *partials, int count, const int *flags, uint8_t *gt_bytes, int *is_one) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     int bad = 0;

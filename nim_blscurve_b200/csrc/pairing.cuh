@@ -143,8 +143,8 @@ BLS_FN int ml_bit(int i) { return (int)((BLS_Z_ABS >> i) & 1); }
 // index of the tangent line of loop iteration i (i = 62..0); the chord of the same iteration, if any, follows it
 BLS_FN int ml_line_index(int i) { return (62 - i) + (i < 62) + (i < 60) + (i < 57) + (i < 48) + (i < 16); }
 // segment j of nseg covers iterations seg_hi >= i >= seg_lo
-BLS_FN int ml_seg_hi(int j, int nseg) { return 62 - (63 * j) / nseg; }
-BLS_FN int ml_seg_lo(int j, int nseg) { return 62 - (63 * (j + 1)) / nseg + 1; }
+BLS_HD int ml_seg_hi(int j, int nseg) { return 62 - (63 * j) / nseg; }
+BLS_HD int ml_seg_lo(int j, int nseg) { return 62 - (63 * (j + 1)) / nseg + 1; }
 
 BLS_FN void line_store(uint32_t *dst, size_t stride, int s, const fp2 &l0, const fp2 &l1, const fp2 &l2) {
     uint32_t *d = dst + (size_t)s * ML_LINE_WORDS * stride;

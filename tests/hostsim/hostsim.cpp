@@ -8,6 +8,7 @@
 #include <string.h>
 #include "../../nim_blscurve_b200/csrc/h2c.cuh"
 #include "../../nim_blscurve_b200/csrc/pairing.cuh"
+#include "../../nim_blscurve_b200/csrc/fpprog.hpp"
 using namespace bls;
 
 extern "C" {
@@ -94,4 +95,55 @@ void hs_aggregate_g2(const g2_aff *p, size_t n, g2_aff *out) {
     for (size_t i = 1; i < n; i++) { g2_jac t; pt_from_affine(t, p[i]); pt_add(acc, acc, t); }
     pt_to_affine(*out, acc);
 }
+
+// ---- fpprog.hpp: execute a compiled tail program on the CPU exactly as k_fp_program does on the device ----
+static void run_program(const std::vector<uint32_t> &w, const fp *in0, const fp *in1, const fp *cst, fp *out0) {
+    const uint32_t nr = w[0], nslots = w[1], nin = w[2], nout = w[3];
+    std::vector<fp> slots(nslots);
+    fp_set_zero(slots[0]);
+    for (uint32_t e = 0; e < nin; e++) {
+        uint32_t sl = w[4 + 2 * e], ref = w[5 + 2 * e], buf = ref >> 24, idx = ref & 0xffffffu;
+        slots[sl] = (buf == 0 ? in0 : (buf == 1 ? in1 : cst))[idx];
+    }
+    const uint32_t *rp = w.data() + 4 + 2 * (nin + nout);
+    for (uint32_t r = 0; r < nr; r++, rp += 32) {
+        fp res[32];
+        for (int l = 0; l < 32; l++) {              // all lanes read before any lane writes (stricter than the device)
+            uint32_t x = rp[l];
+            if (!x) continue;
+            const fp &a = slots[(x >> 10) & 1023], &b = slots[x & 1023];
+            if ((x >> 30) == 1) fp_mul(res[l], a, b); else if ((x >> 30) == 2) fp_add(res[l], a, b); else fp_sub(res[l], a, b);
+        }
+        for (int l = 0; l < 32; l++) if (rp[l]) slots[(rp[l] >> 20) & 1023] = res[l];
+    }
+    const uint32_t *op = w.data() + 4 + 2 * nin;
+    for (uint32_t e = 0; e < nout; e++) out0[op[2 * e + 1] & 0xffffffu] = slots[op[2 * e]];
+}
+static void const_pool(fp *cst) {
+    memcpy(cst + fpprog::CONST_FROB1, FROB1, sizeof(FROB1));
+    memcpy(cst + fpprog::CONST_FROB2, FROB2, sizeof(FROB2));
+    memcpy(cst + fpprog::CONST_FROB3, FROB3, sizeof(FROB3));
+}
+// stats[0..3] = rounds, mul rounds, slots, ops
+int hs_prog_final(const fp12 *partials, int count, fp12 *out, int *stats) {
+    fpprog::Program P = fpprog::build_final(count);
+    if (!P.ok) return 0;
+    fp cst[fpprog::CONST_COUNT];
+    const_pool(cst);
+    run_program(P.words, (const fp *)partials, nullptr, cst, (fp *)out);
+    stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
+    return 1;
+}
+int hs_prog_combine(const fp12 *seg, int nseg, fp12 *out, int *stats) {
+    int len[64];
+    for (int j = 0; j < nseg; j++) len[j] = ml_seg_hi(j, nseg) - ml_seg_lo(j, nseg) + 1;
+    fpprog::Program P = fpprog::build_combine(nseg, len);
+    if (!P.ok) return 0;
+    fp cst[fpprog::CONST_COUNT];
+    const_pool(cst);
+    run_program(P.words, (const fp *)seg, nullptr, cst, (fp *)out);
+    stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
+    return 1;
+}
+void hs_miller_combine(const fp12 *seg, int nseg, fp12 *out) { miller_combine(*out, seg, nseg); }
 }

@@ -22,7 +22,7 @@ P = pr.P
 def hs():
     src = os.path.join(HERE, "hostsim", "hostsim.cpp")
     csrc = os.path.join(os.path.dirname(HERE), "nim_blscurve_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".hpp"))]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-std=c++17", "-o", SO, src], check=True)
     return C.CDLL(SO)
@@ -159,3 +159,28 @@ def test_aggregate_golden(hs):
     # doubling path: the same point twice
     hs.hs_aggregate_g1(buf(pk[:96] * 2), C.c_size_t(2), o1)
     assert pr.g1_from_mem(bytes(o1)) == pr.g1_mul(pr.g1_from_mem(pk[:96]), 2)
+
+
+def test_tail_programs(hs):
+    """fpprog.hpp: the compiled warp-cooperative tail programs (final exponentiation of a product of partials, Horner
+    over Miller-loop segments), executed round by round like k_fp_program, equal the straight-line formulas."""
+    rng = random.Random(11)
+
+    def rnd12():
+        return tuple(tuple((rng.randrange(P), rng.randrange(P)) for _ in range(3)) for _ in range(2))
+    stats = (C.c_int * 4)()
+    for count in (1, 2, 3, 8):
+        parts = [rnd12() for _ in range(count)]
+        r = out(576)
+        assert hs.hs_prog_final(buf(b"".join(f12b(x) for x in parts)), count, r, stats) == 1
+        prod = parts[0]
+        for x in parts[1:]:
+            prod = pr.f12_mul(prod, x)
+        assert f12f(bytes(r)) == pr.final_exp(prod), count
+        assert stats[2] <= 1024 and stats[1] < 1400, list(stats)
+    for nseg in (1, 2, 8, 21, 63):
+        segs = b"".join(f12b(rnd12()) for _ in range(nseg))
+        r, r2 = out(576), out(576)
+        assert hs.hs_prog_combine(buf(segs), nseg, r, stats) == 1
+        hs.hs_miller_combine(buf(segs), nseg, r2)
+        assert bytes(r) == bytes(r2), nseg
