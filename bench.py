@@ -129,7 +129,11 @@ def main():
 
     cache = bg.BatchedBLSVerifierCache(max_sets=S, device=local)
     h = cache.handle
-    stream = torch.cuda.current_stream(dev)
+    # ONE stream for everything in the timed region: torch's H2D copies, the library's kernels and the NCCL
+    # all-gather are issued on it, so they are ordered without host synchronisation.  (torch's default stream has
+    # handle 0, which blsgpu_set_stream reads as "use the context's own stream" - hence a dedicated stream.)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     L.blsgpu_set_stream(h, C.c_void_p(stream.cuda_stream))
 
     # synthetic workload, generated on the device: rank r owns global sets [r*S, (r+1)*S)

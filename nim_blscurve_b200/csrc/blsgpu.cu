@@ -147,6 +147,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
         (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB2, FROB2, sizeof(FROB2), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
         (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB3, FROB3, sizeof(FROB3), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess)
         return bad("cudaMemcpyFromSymbol(FROB)", e);
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bad("cudaDeviceSynchronize", e);
     ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
     for (int i = 0; i <= ST_COUNT; i++) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
@@ -221,7 +222,9 @@ static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &ou
     dp.nslots = P.nslots;
     dp.nrounds = P.nrounds;
     CK(cudaMalloc((void **)&dp.d, P.words.size() * 4));
-    CK(cudaMemcpy(dp.d, P.words.data(), P.words.size() * 4, cudaMemcpyHostToDevice));
+    // stream-ordered upload, completed before the host vector goes away (first use only)
+    CK(cudaMemcpyAsync(dp.d, P.words.data(), P.words.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     cache[key] = dp;
     out = dp;
     return 0;
