@@ -36,7 +36,10 @@ struct blsgpu_ctx {
     g2_jac *d_S = nullptr;
     fp12 *d_F = nullptr;          // per-segment block products, nseg rows
     size_t f_cap = 0;
+    fp12 *d_F2 = nullptr;         // second-level block products
+    size_t f2_cap = 0;
     fp12 *d_seg = nullptr;        // 64 segment products
+    bool acc_team = true;         // six-lane team accumulation (acc_team.cuh) vs one thread per group
     uint32_t *d_lines = nullptr;  // 68 x 72 words x lines_stride
     size_t lines_cap = 0;         // pairs per tile
     fp12 *d_partials = nullptr;   // 64 slots
@@ -94,7 +97,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gtb);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_consts); cudaFree(ctx->d_gt);
     for (auto &kv : ctx->combine_progs) cudaFree(kv.second.d);
-    for (auto &kv : ctx->final_progs) cudaFree(kv.second.d); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines);
+    for (auto &kv : ctx->final_progs) cudaFree(kv.second.d); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i <= ST_COUNT; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
@@ -133,8 +136,10 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     ctx->lines_cap = ((n + 1 < LINES_TILE ? n + 1 : LINES_TILE) + 31) & ~(size_t)31;
     ALLOC(ctx->d_lines, (size_t)ML_NLINES * ML_LINE_WORDS * 4 * ctx->lines_cap);
     // block products: <= 64 segments x (blocks per tile + 1) x tiles
-    ctx->f_cap = 64 * ((n + 1) / BLS_ACC_BS + 2 + (n + 1) / LINES_TILE + 1);
+    ctx->f_cap = (n + 1) / 2 + 40000 + 64 * ((n + 1) / LINES_TILE + 2);   // >= nseg * groups for every miller_shape
     ALLOC(ctx->d_F, ctx->f_cap * sizeof(fp12));
+    ctx->f2_cap = ctx->f_cap / 64 + 4096;
+    ALLOC(ctx->d_F2, ctx->f2_cap * sizeof(fp12));
     ALLOC(ctx->d_seg, 64 * sizeof(fp12));
     ALLOC(ctx->d_partials, 64 * sizeof(fp12));
     ALLOC(ctx->d_gtb, 576);
@@ -149,6 +154,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
         return bad("cudaMemcpyFromSymbol(FROB)", e);
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bad("cudaDeviceSynchronize", e);
     ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
+    if (getenv("BLSGPU_ACC_TEAM")) ctx->acc_team = atoi(getenv("BLSGPU_ACC_TEAM")) != 0;
     for (int i = 0; i <= ST_COUNT; i++) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
         ctx->ev_valid[i] = true;
@@ -243,12 +249,20 @@ static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp 
 
 // Work decomposition of the accumulation: G pairs per group (they share the Fp12 squarings) and nseg loop segments,
 // chosen so that groups x segments gives every SM several warps even for small batches.
-static void miller_shape(size_t np, int &G, int &nseg) {
-    G = 1;
-    while (G < 8 && np / (size_t)(2 * G) >= 8192) G *= 2;
-    size_t ngroups = (np + G - 1) / G;
-    size_t want = ((size_t)1 << 17) / ngroups;
-    nseg = want < 1 ? 1 : (want > 32 ? 32 : (int)want);
+static void miller_shape(size_t np, bool team, int &G, int &nseg) {
+    if (team) {                                    // ~32k teams: 6 lanes each, squarings are cheap to share widely
+        G = 1;
+        while (G < 16 && np / (size_t)(2 * G) >= 4096) G *= 2;
+        size_t ngroups = (np + G - 1) / G;
+        size_t want = ((size_t)1 << 15) / ngroups;
+        nseg = want < 1 ? 1 : (want > 32 ? 32 : (int)want);
+    } else {
+        G = 1;
+        while (G < 8 && np / (size_t)(2 * G) >= 8192) G *= 2;
+        size_t ngroups = (np + G - 1) / G;
+        size_t want = ((size_t)1 << 17) / ngroups;
+        nseg = want < 1 ? 1 : (want > 32 ? 32 : (int)want);
+    }
     if (const char *e = getenv("BLSGPU_MILLER_G")) G = atoi(e);
     if (const char *e = getenv("BLSGPU_MILLER_NSEG")) nseg = atoi(e);
     if (G < 1) G = 1;
@@ -297,14 +311,18 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     ctx->launches += 3;
     // Miller loop over n + 1 pairs, tile by tile: lines, then per-(group, segment) accumulation
     const size_t np = n + 1;
+    const bool team = ctx->acc_team;
     int G, nseg;
-    miller_shape(np < ctx->lines_cap ? np : ctx->lines_cap, G, nseg);
-    size_t ncols = 0;
+    miller_shape(np < ctx->lines_cap ? np : ctx->lines_cap, team, G, nseg);
+    size_t ncols = 0;                                       // entries per segment row of d_F
     for (size_t off = 0; off < np; off += ctx->lines_cap) {
         size_t t = np - off < ctx->lines_cap ? np - off : ctx->lines_cap;
-        ncols += (((t + G - 1) / G) + BLS_ACC_BS - 1) / BLS_ACC_BS;
+        size_t ngroups = (t + G - 1) / G;
+        ncols += team ? ngroups : (ngroups + BLS_ACC_BS - 1) / BLS_ACC_BS;
     }
-    if ((size_t)nseg * ncols > ctx->f_cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "segment product buffer too small");
+    const size_t ncols2 = (ncols + BLS_ACC_BS - 1) / BLS_ACC_BS;
+    if ((size_t)nseg * ncols > ctx->f_cap || (size_t)nseg * ncols2 > ctx->f2_cap)
+        return fail(ctx, BLSGPU_ERR_CAPACITY, "segment product buffer too small");
     size_t col = 0;
     MARK(ST_LINES);
     bool single = np <= ctx->lines_cap;
@@ -314,14 +332,27 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         k_miller_lines<<<nblk(t), 128, 0, s>>>(ctx->d_Q + off, ctx->d_P + off, t, ctx->d_lines, stride);
         if (single) MARK(ST_ACC);
         size_t ngroups = (t + G - 1) / G;
-        dim3 grid(nblk(ngroups, BLS_ACC_BS), nseg);
-        k_miller_acc<<<grid, BLS_ACC_BS, 0, s>>>(ctx->d_lines, stride, t, ngroups, G, nseg, ctx->d_F, ncols, col);
-        col += grid.x;
+        if (team) {
+            dim3 grid(nblk(ngroups, ACC_TPB), nseg);
+            k_miller_acc_team<<<grid, ACC_BS, 0, s>>>(ctx->d_lines, stride, t, ngroups, G, nseg, ctx->d_F, ncols, col);
+            col += ngroups;
+        } else {
+            dim3 grid(nblk(ngroups, BLS_ACC_BS), nseg);
+            k_miller_acc<<<grid, BLS_ACC_BS, 0, s>>>(ctx->d_lines, stride, t, ngroups, G, nseg, ctx->d_F, ncols, col);
+            col += grid.x;
+        }
         ctx->launches += 2;
     }
     if (!single) MARK(ST_ACC);                              // multi-tile: lines+acc are reported together under miller_lines
     MARK(ST_GTPROD);
-    k_fp12_rows<<<nseg, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_seg);
+    if (ncols > BLS_ACC_BS) {
+        dim3 grid((unsigned)ncols2, nseg);
+        k_fp12_rows_step<<<grid, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_F2, ncols2);
+        k_fp12_rows<<<nseg, BLS_ACC_BS, 0, s>>>(ctx->d_F2, ncols2, ncols2, ctx->d_seg);
+        ctx->launches++;
+    } else {
+        k_fp12_rows<<<nseg, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_seg);
+    }
     MARK(ST_PARTIAL);
     ctx->launches++;
     if (ctx->serial_tail) {

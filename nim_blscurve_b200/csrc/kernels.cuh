@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include "h2c.cuh"
 #include "pairing.cuh"
+#include "acc_team.cuh"
 
 namespace bls {
 
@@ -243,6 +244,78 @@ __global__ void __launch_bounds__(BLS_ACC_BS, BLS_ACC_BLOCKS) k_miller_acc(const
     else fp12_set_one(f);
     block_fp12_product(f, sm);
     if (threadIdx.x == 0) Fseg[(size_t)j * row_stride + col_off + blockIdx.x] = f;
+}
+
+// Team version of the accumulation (acc_team.cuh): grid = (ceil(ngroups / ACC_TPB), nseg); every team of six lanes folds
+// the lines of ONE group over ONE segment and writes its Fp12 to Fteam[j * row_stride + col_off + team].
+#ifndef BLS_ACCT_BLOCKS
+#define BLS_ACCT_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(ACC_BS, BLS_ACCT_BLOCKS) k_miller_acc_team(const uint32_t *lines, size_t stride, size_t np,
+                                                                            size_t ngroups, int G, int nseg, fp12 *Fteam,
+                                                                            size_t row_stride, size_t col_off) {
+    __shared__ acc_team_sm sm[ACC_TPB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= 6 * ACC_TPW) return;                       // lanes 30, 31 idle (never reach a barrier)
+    const uint32_t mask = (1u << (6 * ACC_TPW)) - 1;
+    const int team = lane / 6, k = lane % 6;
+    acc_team_sm &T = sm[warp * ACC_TPW + team];
+    const size_t g = ((size_t)blockIdx.x * (ACC_BS / 32) + warp) * ACC_TPW + team;
+    const int j = blockIdx.y, i_hi = ml_seg_hi(j, nseg), i_lo = ml_seg_lo(j, nseg);
+    const bool team_valid = g < ngroups;
+    bool first = true;
+    for (int i = i_hi; i >= i_lo; i--) {
+        if (!first) team_square(T, k, mask);
+        const int s0 = ml_line_index(i), nl = 1 + ml_bit(i);
+        for (int a = 0; a < nl; a++)
+            for (int kk = 0; kk < G; kk++) {
+                // stage the line: lane k fetches Fp number k of the triple (neutral line 1 when the pair does not exist)
+                const size_t p = g + (size_t)kk * ngroups;
+                fp v;
+                if (team_valid && p < np) {
+                    const uint32_t *src = lines + ((size_t)(s0 + a) * ML_LINE_WORDS + 12 * k) * stride + p;
+#pragma unroll
+                    for (int w = 0; w < 12; w++) v.l[w] = src[(size_t)w * stride];
+                } else if (k == 0) {
+                    v = FP_ONE;
+                } else {
+                    fp_set_zero(v);
+                }
+                T.l[k] = v;
+                __syncwarp(mask);
+                if (k < 3) { fp sum; fp_add(sum, T.l[2 * k], T.l[2 * k + 1]); T.l[6 + k] = sum; }
+                __syncwarp(mask);
+                if (first) {                                // f = line: w^0 <- l0, w^2 <- l1, w^3 <- l2
+                    fp c0, c1;
+                    const int li = k == 0 ? 0 : (k == 2 ? 1 : (k == 3 ? 2 : -1));
+                    if (li >= 0) { c0 = T.l[2 * li]; c1 = T.l[2 * li + 1]; } else { fp_set_zero(c0); fp_set_zero(c1); }
+                    team_store_coeff(T, k, c0, c1);
+                    __syncwarp(mask);
+                    first = false;
+                } else {
+                    team_mul_line(T, k, mask);
+                }
+            }
+    }
+    if (team_valid) {                                       // coefficient of w^k is a[k&1][k>>1] of the tower layout
+        fp2 *dst = (fp2 *)&Fteam[(size_t)j * row_stride + col_off + g];
+        fp2 out;
+        out.c0 = T.f[k][FV_C0];
+        out.c1 = T.f[k][FV_C1];
+        dst[3 * (k & 1) + (k >> 1)] = out;
+    }
+}
+
+// pairwise block reduction of rows: grid = (ceil(ncols / 128), nrows); block b of row j multiplies entries
+// [128 b, 128 b + 128) of the row and writes the product to out[j * out_stride + b]
+__global__ void __launch_bounds__(BLS_ACC_BS, BLS_ACC_BLOCKS) k_fp12_rows_step(const fp12 *in, size_t in_stride, size_t ncols,
+                                                                               fp12 *out, size_t out_stride) {
+    __shared__ uint32_t sm[(BLS_ACC_BS / 2) * 144];
+    const size_t c = (size_t)blockIdx.x * BLS_ACC_BS + threadIdx.x;
+    fp12 f;
+    if (c < ncols) f = in[(size_t)blockIdx.y * in_stride + c]; else fp12_set_one(f);
+    block_fp12_product(f, sm);
+    if (threadIdx.x == 0) out[(size_t)blockIdx.y * out_stride + blockIdx.x] = f;
 }
 
 // one block per segment row: product of ncols values -> seg[j]
