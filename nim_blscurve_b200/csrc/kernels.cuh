@@ -19,9 +19,9 @@
 
 namespace bls {
 
-// heavy kernels: at most 128 registers -> 4 blocks of 128 threads (16 warps) per SM
+// heavy kernels: at most 128 registers -> 4 blocks of 128 threads (16 warps, 4 per scheduler) per SM
 #ifndef BLS_LB_BLOCKS
-#define BLS_LB_BLOCKS 2
+#define BLS_LB_BLOCKS 4
 #endif
 #define BLS_LB __launch_bounds__(128, BLS_LB_BLOCKS)
 
@@ -197,7 +197,7 @@ __global__ void k_sig_pair(const g2_jac *S, size_t n, g2_aff *Q, g1_aff *P) {
 }
 
 #ifndef BLS_LINES_BLOCKS
-#define BLS_LINES_BLOCKS 2
+#define BLS_LINES_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, BLS_LINES_BLOCKS) k_miller_lines(const g2_aff *Q, const g1_aff *P, size_t np,
                                                                        uint32_t *lines, size_t stride) {
