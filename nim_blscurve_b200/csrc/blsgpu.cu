@@ -49,8 +49,10 @@ struct blsgpu_ctx {
     size_t misc_bytes = 0;
     void *d_misc2 = nullptr;      // small result scratch (MSM output)
     uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
-    cudaEvent_t ev[ST_COUNT + 1];
-    bool ev_valid[ST_COUNT + 1];
+    cudaEvent_t ev[2 * ST_COUNT + 2];                        // stage begin/end pairs + fork/join
+    bool ev_valid[2 * ST_COUNT + 2];
+    cudaStream_t side = nullptr;                             // the signature-side MSM runs beside the per-set stages
+    bool use_side = true;
     float stage_ms[ST_COUNT];
     int launches = 0;
     msm_state msm;
@@ -100,7 +102,8 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     for (auto &kv : ctx->final_progs) cudaFree(kv.second.d); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (int i = 0; i <= ST_COUNT; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2 * ST_COUNT + 2; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -113,7 +116,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     blsgpu_ctx *ctx = new blsgpu_ctx();
     ctx->device = device;
     ctx->cap = max_sets;
-    for (int i = 0; i <= ST_COUNT; i++) ctx->ev_valid[i] = false;
+    for (int i = 0; i < 2 * ST_COUNT + 2; i++) ctx->ev_valid[i] = false;
     for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
     cudaError_t e = cudaSetDevice(device);
     auto bad = [&](const char *what, cudaError_t err) {
@@ -155,10 +158,12 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bad("cudaDeviceSynchronize", e);
     ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
     if (getenv("BLSGPU_ACC_TEAM")) ctx->acc_team = atoi(getenv("BLSGPU_ACC_TEAM")) != 0;
-    for (int i = 0; i <= ST_COUNT; i++) {
+    for (int i = 0; i < 2 * ST_COUNT + 2; i++) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
         ctx->ev_valid[i] = true;
     }
+    if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
+    if (getenv("BLSGPU_SIDE_STREAM")) ctx->use_side = atoi(getenv("BLSGPU_SIDE_STREAM")) != 0;
     return ctx;
 }
 
@@ -191,7 +196,10 @@ static words8 words_of(const uint8_t b[32]) {
     return w;
 }
 
-#define MARK(stage) CK(cudaEventRecord(ctx->ev[stage], s))
+#define BEGIN(stage, st) CK(cudaEventRecord(ctx->ev[2 * (stage)], st))
+#define END(stage, st) CK(cudaEventRecord(ctx->ev[2 * (stage) + 1], st))
+#define EV_FORK (2 * ST_COUNT)
+#define EV_JOIN (2 * ST_COUNT + 1)
 
 // scalars for global indices [first, first+n) into d_r
 static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size_t first, size_t total_n,
@@ -276,39 +284,55 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     cudaStream_t s = ctx->stream;
     ctx->launches = 0;
     CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
-    MARK(ST_SCALARS);
+    BEGIN(ST_SCALARS, s);
     int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars);
     if (rc) return rc;
-    MARK(ST_G2MUL);
+    END(ST_SCALARS, s);
+    // fork: the signature-side sum only needs the scalars; it is latency-bound (bucket reduction, Horner) and hides
+    // behind the per-set stages on a second stream, joined before the Miller-loop lines
+    cudaStream_t g = ctx->use_side ? ctx->side : s;
+    if (ctx->use_side) {
+        CK(cudaEventRecord(ctx->ev[EV_FORK], s));
+        CK(cudaStreamWaitEvent(g, ctx->ev[EV_FORK], 0));
+    }
+    BEGIN(ST_G2MUL, g);
     // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
     // buckets, n independent 64-bit multiplications + tree below that
     static const size_t g2_msm_min = getenv("BLSGPU_G2_MSM_MIN") ? (size_t)atoll(getenv("BLSGPU_G2_MSM_MIN")) : 2048;
     if (n >= g2_msm_min) {
         std::string err;
         rc = msm_run<fp2>(ctx->msm, (const uint8_t *)d_sets + offsetof(sigset, sig), sizeof(sigset), (const uint8_t *)ctx->d_r, 8,
-                          n, 64, s, ctx->d_S, nullptr, &ctx->launches, err);
+                          n, 64, g, ctx->d_S, nullptr, &ctx->launches, err);
         if (rc) return fail(ctx, rc == -1 ? BLSGPU_ERR_CUDA : BLSGPU_ERR_ARG, err.c_str());
-        MARK(ST_G2SUM);
+        END(ST_G2MUL, g);
+        BEGIN(ST_G2SUM, g);
     } else {
-        k_g2_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_S);
+        k_g2_mul<<<nblk(n), 128, 0, g>>>(d_sets, ctx->d_r, n, ctx->d_S);
         ctx->launches++;
-        MARK(ST_G2SUM);
+        END(ST_G2MUL, g);
+        BEGIN(ST_G2SUM, g);
         for (size_t m = n; m > 1;) {
             size_t half = (m + 1) / 2;
-            k_g2_tree<<<nblk(half), 128, 0, s>>>(ctx->d_S, m, half);
+            k_g2_tree<<<nblk(half), 128, 0, g>>>(ctx->d_S, m, half);
             ctx->launches++;
             m = half;
         }
     }
-    k_sig_pair<<<1, 32, 0, s>>>(ctx->d_S, n, ctx->d_Q, ctx->d_P);
+    k_sig_pair<<<1, 32, 0, g>>>(ctx->d_S, n, ctx->d_Q, ctx->d_P);
     ctx->launches++;
-    MARK(ST_HASH);
+    END(ST_G2SUM, g);
+    if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_JOIN], g));
+    BEGIN(ST_HASH, s);
     k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
-    MARK(ST_G1MUL);
+    END(ST_HASH, s);
+    BEGIN(ST_G1MUL, s);
     k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
-    MARK(ST_AFFINE);
+    END(ST_G1MUL, s);
+    BEGIN(ST_AFFINE, s);
     k_pairs_affine<<<nblk(n), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P);
+    END(ST_AFFINE, s);
     ctx->launches += 3;
+    if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));   // join: pair number n is in place
     // Miller loop over n + 1 pairs, tile by tile: lines, then per-(group, segment) accumulation
     const size_t np = n + 1;
     const bool team = ctx->acc_team;
@@ -324,13 +348,13 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     if ((size_t)nseg * ncols > ctx->f_cap || (size_t)nseg * ncols2 > ctx->f2_cap)
         return fail(ctx, BLSGPU_ERR_CAPACITY, "segment product buffer too small");
     size_t col = 0;
-    MARK(ST_LINES);
+    BEGIN(ST_LINES, s);
     bool single = np <= ctx->lines_cap;
     for (size_t off = 0; off < np; off += ctx->lines_cap) {
         size_t t = np - off < ctx->lines_cap ? np - off : ctx->lines_cap;
         size_t stride = ctx->lines_cap;
         k_miller_lines<<<nblk(t), 128, 0, s>>>(ctx->d_Q + off, ctx->d_P + off, t, ctx->d_lines, stride);
-        if (single) MARK(ST_ACC);
+        if (single) { END(ST_LINES, s); BEGIN(ST_ACC, s); }
         size_t ngroups = (t + G - 1) / G;
         if (team) {
             dim3 grid(nblk(ngroups, ACC_TPB), nseg);
@@ -343,8 +367,9 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         }
         ctx->launches += 2;
     }
-    if (!single) MARK(ST_ACC);                              // multi-tile: lines+acc are reported together under miller_lines
-    MARK(ST_GTPROD);
+    if (!single) { END(ST_LINES, s); BEGIN(ST_ACC, s); }    // multi-tile: lines+acc are reported together under miller_lines
+    END(ST_ACC, s);
+    BEGIN(ST_GTPROD, s);
     if (ncols > BLS_ACC_BS) {
         dim3 grid((unsigned)ncols2, nseg);
         k_fp12_rows_step<<<grid, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_F2, ncols2);
@@ -353,7 +378,8 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     } else {
         k_fp12_rows<<<nseg, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_seg);
     }
-    MARK(ST_PARTIAL);
+    END(ST_GTPROD, s);
+    BEGIN(ST_PARTIAL, s);
     ctx->launches++;
     if (ctx->serial_tail) {
         k_combine<<<1, 32, 0, s>>>(ctx->d_seg, nseg, ctx->d_partials + slot);
@@ -365,7 +391,7 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         rc = launch_prog(ctx, cp, (const fp *)ctx->d_seg, (fp *)(ctx->d_partials + slot));
         if (rc) return rc;
     }
-    MARK(ST_FINAL);
+    END(ST_PARTIAL, s);
     CK(cudaGetLastError());
     return 0;
 }
@@ -374,6 +400,7 @@ static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_in
                      const int *d_rank_flags = nullptr) {
     cudaStream_t s = ctx->stream;
     const fp12 *parts = d_partials ? d_partials : ctx->d_partials;
+    BEGIN(ST_FINAL, s);
     if (ctx->serial_tail) {
         k_final<<<1, 32, 0, s>>>(parts, count, d_rank_flags, ctx->d_gtb, ctx->d_flags + 1);
         ctx->launches++;
@@ -386,7 +413,7 @@ static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_in
         k_final_out<<<1, 32, 0, s>>>(ctx->d_gt, count, d_rank_flags, ctx->d_gtb, ctx->d_flags + 1);
         ctx->launches++;
     }
-    CK(cudaEventRecord(ctx->ev[ST_COUNT], s));
+    END(ST_FINAL, s);
     CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_gtb, 576, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_pinned + 576, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -401,7 +428,7 @@ static void collect_stage_times(blsgpu_ctx *ctx, bool with_final) {
     for (int i = 0; i < ST_COUNT; i++) {
         float ms = 0.f;
         if (i == ST_FINAL && !with_final) { ctx->stage_ms[i] = 0.f; continue; }
-        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+        if (cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
         ctx->stage_ms[i] = ms;
     }
 }
@@ -511,7 +538,6 @@ extern "C" int blsgpu_finalize_dev(blsgpu_ctx *ctx, const void *d_partials, size
     if (gt_out) memset(gt_out, 0, 576);
     if (count == 0) return 0;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaEventRecord(ctx->ev[ST_FINAL], ctx->stream));
     int bad = 0;
     int rc = run_final(ctx, (int)count, gt_out, &bad, (const fp12 *)d_partials, d_flags);
     collect_stage_times(ctx, true);
@@ -528,10 +554,9 @@ extern "C" int blsgpu_finalize(blsgpu_ctx *ctx, const uint8_t *partials, size_t 
     CK(cudaSetDevice(ctx->device));
     ctx->launches = 0;
     CK(cudaMemcpyAsync(ctx->d_partials, partials, count * 576, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[ST_FINAL], ctx->stream));
     int rc = run_final(ctx, (int)count, gt_out, nullptr);
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev[ST_FINAL], ctx->ev[ST_COUNT]) == cudaSuccess) ctx->stage_ms[ST_FINAL] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[2 * ST_FINAL], ctx->ev[2 * ST_FINAL + 1]) == cudaSuccess) ctx->stage_ms[ST_FINAL] = ms;
     return rc;
 }
 
