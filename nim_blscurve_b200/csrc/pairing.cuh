@@ -83,6 +83,74 @@ BLS_NOINLINE void line_add(g2_jac &T, const g2_aff &Q, fp2 &l0, fp2 &l1p, fp2 &l
     l2p = T.z;
 }
 
+// The same two steps on HOMOGENEOUS projective coordinates (x = X/Z, y = Y/Z), the form the split Miller loop uses:
+// tangent 2M + 7S instead of 5M + 6S (Costello-Lange-Naehrig, a = 0, b' = 4 xi).  With B = Y^2, C = Z^2, E = 3 b' C,
+// the tangent scaled by 2YZ^2 / Z is  (B - E) + 3X^2 (-x_P) v + 2YZ y_P (v w); the doubled point is taken times 4
+// (a projective rescale) so that no halving is needed:
+//     X3 = 2XY (B - 3E),  Y3 = (B + 3E)^2 - 12 E^2,  Z3 = 4 B * 2YZ.
+BLS_NOINLINE void line_dbl_proj(g2_jac &T, fp2 &l0, fp2 &l1p, fp2 &l2p) {
+    fp2 A2, B, C, E, F, H, J, t, u;
+    fp2_sqr(B, T.y);
+    fp2_sqr(C, T.z);
+    fp2_sqr(J, T.x);
+    fp2_add(t, T.x, T.y);
+    fp2_sqr(A2, t);
+    fp2_sub(A2, A2, J);
+    fp2_sub(A2, A2, B);                   // 2XY
+    fp2_add(t, T.y, T.z);
+    fp2_sqr(H, t);
+    fp2_sub(H, H, B);
+    fp2_sub(H, H, C);                     // 2YZ
+    fp2_mul_xi(E, C);
+    fp2_dbl(E, E);
+    fp2_dbl(E, E);
+    fp2_mul3(E, E);                       // E = 12 xi Z^2 = 3 b' Z^2
+    fp2_mul3(F, E);                       // 3E
+    fp2_sub(l0, B, E);
+    fp2_mul3(l1p, J);                     // 3X^2            (times -x_P)
+    l2p = H;                              // 2YZ             (times y_P)
+    fp2_sub(t, B, F);
+    fp2_mul(T.x, A2, t);
+    fp2_add(t, B, F);
+    fp2_sqr(t, t);
+    fp2_dbl(u, E);
+    fp2_sqr(u, u);
+    fp2_mul3(u, u);                       // 12 E^2
+    fp2_sub(T.y, t, u);
+    fp2_mul(t, B, H);
+    fp2_dbl(t, t);
+    fp2_dbl(T.z, t);
+}
+
+// chord through T and the affine Q, T <- T + Q: theta = Y - y_Q Z, lambda = X - x_Q Z,
+// line = (theta x_Q - lambda y_Q) + theta (-x_P) v + lambda y_P (v w)          (11M + 2S)
+BLS_NOINLINE void line_add_proj(g2_jac &T, const g2_aff &Q, fp2 &l0, fp2 &l1p, fp2 &l2p) {
+    fp2 th, la, c, d, e, f, g, h, t;
+    fp2_mul(t, Q.y, T.z);
+    fp2_sub(th, T.y, t);
+    fp2_mul(t, Q.x, T.z);
+    fp2_sub(la, T.x, t);
+    fp2_sqr(c, th);
+    fp2_sqr(d, la);
+    fp2_mul(e, la, d);
+    fp2_mul(f, T.z, c);
+    fp2_mul(g, T.x, d);
+    fp2_add(h, e, f);
+    fp2_sub(h, h, g);
+    fp2_sub(h, h, g);
+    fp2_mul(T.x, la, h);
+    fp2_sub(t, g, h);
+    fp2_mul(t, th, t);
+    fp2_mul(g, e, T.y);
+    fp2_sub(T.y, t, g);
+    fp2_mul(T.z, T.z, e);
+    fp2_mul(l0, th, Q.x);
+    fp2_mul(t, la, Q.y);
+    fp2_sub(l0, l0, t);
+    l1p = th;
+    l2p = la;
+}
+
 BLS_FN void line_apply(fp12 &f, const fp2 &l0, const fp2 &l1p, const fp2 &l2p, const fp &neg_px, const fp &py) {
     fp2 l1, l2;
     fp2_mul_fp(l1, l1p, neg_px);
@@ -187,12 +255,12 @@ BLS_NOINLINE void miller_lines(const g2_aff &Q, const g1_aff &P, uint32_t *dst, 
     fp_neg(npx, P.x);
     int s = 0;
     for (int i = 62; i >= 0; i--) {
-        line_dbl(T, l0, l1, l2);
+        line_dbl_proj(T, l0, l1, l2);
         fp2_mul_fp(l1, l1, npx);
         fp2_mul_fp(l2, l2, py);
         line_store(dst, stride, s++, l0, l1, l2);
         if (ml_bit(i)) {
-            line_add(T, Q, l0, l1, l2);
+            line_add_proj(T, Q, l0, l1, l2);
             fp2_mul_fp(l1, l1, npx);
             fp2_mul_fp(l2, l2, py);
             line_store(dst, stride, s++, l0, l1, l2);
