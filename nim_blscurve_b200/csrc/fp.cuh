@@ -29,7 +29,9 @@
 
 namespace bls {
 
-struct fp { uint32_t l[12]; };
+// 16-byte alignment: every field element moves as three 128-bit accesses (local, shared, global).  All containing
+// layouts keep their reference sizes and offsets (48 = 3 x 16; SignatureSet: pk @0, msg @96, sig @128).
+struct alignas(16) fp { uint32_t l[12]; };
 
 // p = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
 // (vendor/blst/src/consts.c:10-14).  A switch so that unrolled loops fold the limbs into immediates.
