@@ -113,37 +113,64 @@ __global__ void BLS_LB k_g1_mul(const sigset *sets, const uint64_t *r, size_t n,
     g1_aff pk = sets[i].pk;
     if (aff_is_inf(pk)) atomicOr(flags, 1);            // BLST_PK_IS_INFINITY (aggregate.c:296)
     g1_jac j;
-    pt_mul_u64(j, pk, r[i]);
+    pt_mul_u64_w4(j, pk, r[i]);
     Pj[i] = j;
 }
 
-// H_i and [r_i]pk_i to affine with ONE Fermat inversion per set (Montgomery's trick on N(Z_H) and Z_P)
+// H_i and [r_i]pk_i to affine.  Montgomery's trick twice over: per set the two denominators N(Z_H) and Z_P share
+// one inverse, and every thread walks AFF_B sets (strided by the thread count, so that warps stay coalesced) and
+// shares ONE Fermat inversion among them: 1 inversion + ~45 multiplications per set become 1/8 inversion + ~50.
+#define AFF_B 8
 __global__ void BLS_LB k_pairs_affine(const g2_jac *H, const g1_jac *Pj, size_t n, g2_aff *Q, g1_aff *P) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    g2_jac h = H[i];
-    g1_jac p = Pj[i];
-    fp nz, t, zp = p.z, prod, inv, ninv, zpinv;
-    fp_sqr_ni(nz, h.z.c0);
-    fp_sqr_ni(t, h.z.c1);
-    fp_add(nz, nz, t);                                  // N(Z_H)
-    bool h_inf = fp_is_zero(nz), p_inf = fp_is_zero(zp);
-    if (h_inf) nz = FP_ONE;
-    if (p_inf) zp = FP_ONE;
-    fp_mul_ni(prod, nz, zp);
-    fp_inv(inv, prod);
-    fp_mul_ni(ninv, inv, zp);                           // 1/N(Z_H)
-    fp_mul_ni(zpinv, inv, nz);                          // 1/Z_P
-    fp2 zhinv;
-    fp_mul_ni(zhinv.c0, h.z.c0, ninv);
-    fp_mul_ni(t, h.z.c1, ninv);
-    fp_neg(zhinv.c1, t);
-    g2_aff q;
-    g1_aff a;
-    pt_to_affine_zinv(q, h, zhinv);
-    pt_to_affine_zinv(a, p, zpinv);
-    Q[i] = q;
-    P[i] = a;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    if (t >= n) return;
+    fp nz[AFF_B], zp[AFF_B], pre[AFF_B];
+    int cnt = 0;
+    for (int k = 0; k < AFF_B; k++) {
+        const size_t i = t + (size_t)k * nthreads;
+        if (i >= n) break;
+        fp2 hz = H[i].z;
+        fp a, b;
+        fp_sqr_ni(a, hz.c0);
+        fp_sqr_ni(b, hz.c1);
+        fp_add(a, a, b);                                    // N(Z_H)
+        b = Pj[i].z;
+        if (fp_is_zero(a)) a = FP_ONE;                      // infinity: keep the product invertible
+        if (fp_is_zero(b)) b = FP_ONE;
+        nz[k] = a;
+        zp[k] = b;
+        fp c;
+        fp_mul_ni(c, a, b);
+        if (k) fp_mul_ni(pre[k], pre[k - 1], c); else pre[k] = c;
+        cnt = k + 1;
+    }
+    fp inv;
+    fp_inv(inv, pre[cnt - 1]);
+    for (int k = cnt - 1; k >= 0; k--) {
+        const size_t i = t + (size_t)k * nthreads;
+        fp ik, ninv, zpinv, tt;
+        if (k) {
+            fp_mul_ni(ik, inv, pre[k - 1]);                 // 1 / (N(Z_H) Z_P) of set k
+            fp_mul_ni(tt, nz[k], zp[k]);
+            fp_mul_ni(inv, inv, tt);
+        } else {
+            ik = inv;
+        }
+        fp_mul_ni(ninv, ik, zp[k]);                         // 1/N(Z_H)
+        fp_mul_ni(zpinv, ik, nz[k]);                        // 1/Z_P
+        g2_jac h = H[i];
+        g1_jac p = Pj[i];
+        fp2 zhinv;
+        fp_mul_ni(zhinv.c0, h.z.c0, ninv);
+        fp_mul_ni(tt, h.z.c1, ninv);
+        fp_neg(zhinv.c1, tt);
+        g2_aff q;
+        g1_aff a;
+        pt_to_affine_zinv(q, h, zhinv);                     // infinity (Z = 0) -> all-zero affine
+        pt_to_affine_zinv(a, p, zpinv);
+        Q[i] = q;
+        P[i] = a;
+    }
 }
 
 __global__ void BLS_LB k_g2_mul(const sigset *sets, const uint64_t *r, size_t n, g2_jac *S) {

@@ -24,6 +24,7 @@ void hs_hash_to_g2(const uint8_t *msg, size_t len, const uint8_t *dst, uint32_t 
     g2_compress(comp, *aff);
 }
 void hs_g1_mul_u64(const g1_aff *p, uint64_t k, g1_aff *r) { g1_jac j; pt_mul_u64(j, *p, k); pt_to_affine(*r, j); }
+void hs_g1_mul_u64_w4(const g1_aff *p, uint64_t k, g1_aff *r) { g1_jac j; pt_mul_u64_w4(j, *p, k); pt_to_affine(*r, j); }
 void hs_g2_mul_u64(const g2_aff *p, uint64_t k, g2_aff *r) { g2_jac j; pt_mul_u64(j, *p, k); pt_to_affine(*r, j); }
 
 void hs_fp12_mul(const fp12 *a, const fp12 *b, fp12 *r) { fp12_mul(*r, *a, *b); }
@@ -53,7 +54,7 @@ int hs_batch_verify(const hs_sigset *sets, size_t n, const uint64_t *r, int grou
     for (size_t i = 0; i < n; i++) {
         g2_jac h; hash_to_g2_jac(h, sets[i].msg, 32, dst, 43);
         if (aff_is_inf(sets[i].pk)) pk_inf = 1;
-        g1_jac pj; pt_mul_u64(pj, sets[i].pk, r[i]);
+        g1_jac pj; pt_mul_u64_w4(pj, sets[i].pk, r[i]);
         pt_to_affine(Q[i], h);
         pt_to_affine(P[i], pj);
         g2_jac sj; pt_mul_u64(sj, sets[i].sig, r[i]);

@@ -184,3 +184,23 @@ def test_tail_programs(hs):
         assert hs.hs_prog_combine(buf(segs), nseg, r, stats) == 1
         hs.hs_miller_combine(buf(segs), nseg, r2)
         assert bytes(r) == bytes(r2), nseg
+
+
+def test_g1_mul_windowed(hs):
+    """pt_mul_u64_w4 (signed 4-bit windows) == pt_mul_u64 (double-and-add) == pyref, incl. edge scalars and infinity."""
+    rng = random.Random(5)
+    a = json.load(open(os.path.join(GOLD, "aggregate.json")))
+    pk = bytes.fromhex(a["pubkeys"])[:96]
+    pt = pr.g1_from_mem(pk)
+    ks = [1, 2, 8, 9, 15, 16, 0x8888888888888888, 0x9999999999999999, 0xffffffffffffffff, 0x7777777777777777, 0] + \
+         [rng.getrandbits(64) for _ in range(12)]
+    for k in ks:
+        o1, o2 = out(96), out(96)
+        hs.hs_g1_mul_u64_w4(buf(pk), C.c_uint64(k), o1)
+        hs.hs_g1_mul_u64(buf(pk), C.c_uint64(k), o2)
+        assert bytes(o1) == bytes(o2), hex(k)
+        if k:
+            assert pr.g1_from_mem(bytes(o1)) == pr.g1_mul(pt, k), hex(k)
+    o1 = out(96)
+    hs.hs_g1_mul_u64_w4(buf(bytes(96)), C.c_uint64(12345), o1)
+    assert bytes(o1) == bytes(96)
