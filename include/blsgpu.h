@@ -123,6 +123,14 @@ int blsgpu_msm_g2(blsgpu_ctx *ctx, const void *points192, const void *scalars, s
 int blsgpu_msm_g2_dev(blsgpu_ctx *ctx, const void *d_points192, const void *d_scalars, size_t n, size_t nbits,
                       uint8_t out192[192]);
 
+/* MultiSignatureSet.combine (blscurve/bls_batch_verifier.nim:100-106 -> blst_min_pubkey_sig_core.nim:570-647): the
+ * random linear combination of n (public key, signature) pairs on ONE message, with the reference's scalar order
+ * (SHA-256 chain on secureRandomBytes, four 64-bit scalars per digest taken last-first, zeros skipped) and its two
+ * Pippenger calls (nbits = 64).  n == 1 copies the pair; n == 0 is an error (raiseAssert in the reference).
+ * Returns 1 and the affine pair (96 + 192 bytes). */
+int blsgpu_combine(blsgpu_ctx *ctx, const uint8_t srb[32], const void *pubkeys96, const void *sigs192, size_t n,
+                   uint8_t pk_out[96], uint8_t sig_out[192]);
+
 /* Per-stage device times (ms) of the last batch_verify/partial call on this context, measured with CUDA
  * events on the call's stream.  Returns the number of stages written (<= max); names via blsgpu_stage_name. */
 int blsgpu_last_stage_ms(const blsgpu_ctx *ctx, float *ms, int max);

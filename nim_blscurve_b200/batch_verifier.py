@@ -173,6 +173,46 @@ def msmG2(cache: BatchedBLSVerifierCache, points192: bytes, scalars: bytes, nbit
     return bytes(out)
 
 
+class MultiSignatureSet:
+    """Signatures that all pertain to the same message (bls_batch_verifier.nim:47-62, init :73-91, add :93-98)."""
+
+    def __init__(self, pubkeys: Sequence[bytes], message: bytes, signatures: Sequence[bytes]):
+        assert len(pubkeys) == len(signatures) and len(pubkeys) > 0
+        self.pubkeys, self.message, self.signatures = list(pubkeys), message, list(signatures)
+
+    @classmethod
+    def init(cls, *args):
+        if len(args) == 1:                                   # init(T, sigset)
+            ss = args[0] if isinstance(args[0], SignatureSet) else SignatureSet(*args[0])
+            return cls([ss.pubkey], ss.message, [ss.signature])
+        return cls(*args)
+
+    def add(self, sigset):
+        ss = sigset if isinstance(sigset, SignatureSet) else SignatureSet(*sigset)
+        assert ss.message == self.message
+        self.pubkeys.append(ss.pubkey)
+        self.signatures.append(ss.signature)
+
+    def combine(self, cache: "BatchedBLSVerifierCache", secureRandomBytes: bytes) -> SignatureSet:
+        """bls_batch_verifier.nim:100-106: one SignatureSet = random linear combination of the members."""
+        pk, sig = combine(cache, secureRandomBytes, self.pubkeys, self.signatures)
+        return SignatureSet(pk, self.message, sig)
+
+
+def combine(cache: BatchedBLSVerifierCache, secureRandomBytes: bytes, publicKeys: Sequence[bytes],
+            signatures: Sequence[bytes]):
+    """blst_min_pubkey_sig_core.nim:570-647 on the device: (sum r_i pk_i, sum r_i sig_i), both affine."""
+    assert len(publicKeys) == len(signatures)
+    n = len(publicKeys)
+    if n == 0:
+        raise AssertionError("Must provide at least 1 signature")
+    pk, sig = (C.c_uint8 * 96)(), (C.c_uint8 * 192)()
+    rc = lib().blsgpu_combine(cache.handle, secureRandomBytes, b"".join(publicKeys), b"".join(signatures), n, pk, sig)
+    if rc < 0:
+        raise BlsGpuError(f"combine failed ({rc}): {cache.last_error()}")
+    return bytes(pk), bytes(sig)
+
+
 def rlcScalars(cache: BatchedBLSVerifierCache, srb: bytes, n: int, chunks: int):
     out = (C.c_uint64 * n)()
     rc = lib().blsgpu_rlc_scalars(cache.handle, srb, n, chunks, out)

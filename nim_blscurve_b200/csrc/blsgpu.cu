@@ -677,6 +677,38 @@ extern "C" int blsgpu_msm_g2(blsgpu_ctx *ctx, const void *points192, const void 
     return msm_api_host<fp2>(ctx, points192, scalars, n, nbits, out192);
 }
 
+extern "C" int blsgpu_combine(blsgpu_ctx *ctx, const uint8_t srb[32], const void *pubkeys96, const void *sigs192, size_t n,
+                              uint8_t pk_out[96], uint8_t sig_out[192]) {
+    if (!ctx || !srb || !pubkeys96 || !sigs192 || !pk_out || !sig_out) return BLSGPU_ERR_ARG;
+    if (n == 0) return fail(ctx, BLSGPU_ERR_ARG, "combine: must provide at least 1 signature");   // raiseAssert in the reference
+    if (n == 1) { memcpy(pk_out, pubkeys96, 96); memcpy(sig_out, sigs192, 192); return 1; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int rc = ensure_misc(ctx, n * (96 + 192 + 8) + 1024);
+    if (rc) return rc;
+    rc = ensure_misc2(ctx, 1024);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    uint8_t *d_sig = base, *d_pk = base + n * 192, *d_sc = base + n * (192 + 96);   // 16-byte aligned blocks
+    d_sc = (uint8_t *)(((uintptr_t)d_sc + 15) & ~(uintptr_t)15);
+    CK(cudaMemcpyAsync(d_pk, pubkeys96, n * 96, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_sig, sigs192, n * 192, cudaMemcpyHostToDevice, s));
+    ctx->launches = 1;
+    k_combine_scalars<<<1, 32, 0, s>>>(words_of(srb), n, (uint64_t *)d_sc);
+    std::string err;
+    g1_aff *o1 = (g1_aff *)ctx->d_misc2;
+    g2_aff *o2 = (g2_aff *)((uint8_t *)ctx->d_misc2 + 256);
+    rc = msm_run<fp>(ctx->msm, d_pk, 96, d_sc, 8, n, 64, s, nullptr, o1, &ctx->launches, err);
+    if (!rc) rc = msm_run<fp2>(ctx->msm, d_sig, 192, d_sc, 8, n, 64, s, nullptr, o2, &ctx->launches, err);
+    if (rc) return fail(ctx, rc == -1 ? BLSGPU_ERR_CUDA : BLSGPU_ERR_ARG, err.c_str());
+    CK(cudaMemcpyAsync(ctx->h_pinned, o1, 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_pinned + 256, o2, 192, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(pk_out, ctx->h_pinned, 96);
+    memcpy(sig_out, ctx->h_pinned + 256, 192);
+    return 1;
+}
+
 extern "C" int blsgpu_msm_make_inputs(blsgpu_ctx *ctx, uint64_t seed, size_t n, void *d_points96, void *d_scalars32) {
     if (!ctx || !d_points96 || !d_scalars32) return BLSGPU_ERR_ARG;
     if (n == 0) return 0;

@@ -96,6 +96,28 @@ __global__ void k_rlc_scalars(words8 srb, size_t total_n, uint32_t chunks, size_
     }
 }
 
+// Blinding scalars of MultiSignatureSet.combine (blst_min_pubkey_sig_core.nim:590-606): seed <- SHA256(seed), the
+// digest is read as four little-endian u64 and consumed from the LAST one down; zeros are skipped.  Sequential chain.
+__global__ void k_combine_scalars(words8 srb, size_t n, uint64_t *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t seed[8];
+    for (int k = 0; k < 8; k++) seed[k] = srb.w[k];
+    int avail = 0;
+    for (size_t i = 0; i < n; i++) {
+        for (;;) {
+            if (avail == 0) {
+                uint32_t t[8];
+                sha256_of_32(t, seed);
+                for (int k = 0; k < 8; k++) seed[k] = t[k];
+                avail = 4;
+            }
+            avail--;
+            uint64_t v = le64_of_be_words(seed + 2 * avail);
+            if (v != 0) { out[i] = v; break; }
+        }
+    }
+}
+
 __global__ void BLS_LB k_hash_sets(const sigset *sets, size_t n, g2_jac *H) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -61,6 +61,36 @@ proc batchVerify*(tp: Taskpool, input: openArray[SignatureSet], secureRandomByte
   var cache = BatchedBLSVerifierCache.init(tp, maxSets = max(1, input.len))
   tp.batchVerify(cache, input, secureRandomBytes)
 
+type
+  MultiSignatureSet* = object                                # bls_batch_verifier.nim:47-62
+    pubkeys: seq[PublicKey]
+    message: array[32, byte]
+    signatures: seq[Signature]
+
+func init*(T: type MultiSignatureSet, pubkeys: seq[PublicKey], message: array[32, byte],
+           signatures: seq[Signature]): MultiSignatureSet =
+  doAssert pubkeys.len == signatures.len
+  doAssert pubkeys.len > 0
+  MultiSignatureSet(pubkeys: pubkeys, message: message, signatures: signatures)
+
+func init*(T: type MultiSignatureSet, sigset: SignatureSet): MultiSignatureSet =
+  MultiSignatureSet(pubkeys: @[sigset.pubkey], message: sigset.message, signatures: @[sigset.signature])
+
+func add*(multiSet: var MultiSignatureSet, sigset: SignatureSet) =
+  doAssert multiSet.message == sigset.message
+  multiSet.pubkeys.add sigset.pubkey
+  multiSet.signatures.add sigset.signature
+
+func combine*(cache: var BatchedBLSVerifierCache, multiSet: MultiSignatureSet,
+              secureRandomBytes: array[32, byte]): SignatureSet =
+  ## bls_batch_verifier.nim:100-106 / blst_min_pubkey_sig_core.nim:570-647 on the device
+  doAssert multiSet.pubkeys.len > 0, "Must provide at least 1 signature"
+  result.message = multiSet.message
+  let rc = blsgpu_combine(cache.ctx, unsafeAddr secureRandomBytes, unsafeAddr multiSet.pubkeys[0],
+                          unsafeAddr multiSet.signatures[0], multiSet.pubkeys.len.csize_t,
+                          addr result.pubkey, addr result.signature)
+  doAssert rc == 1, "blsgpu_combine failed"
+
 func aggregateAll*(cache: var BatchedBLSVerifierCache, dst: var PublicKey, elems: openArray[PublicKey]): bool =
   if elems.len == 0: return false                            # blst_min_pubkey_sig_core.nim:183-184
   blsgpu_aggregate_g1(cache.ctx, unsafeAddr elems[0], elems.len.csize_t, addr dst) == 1

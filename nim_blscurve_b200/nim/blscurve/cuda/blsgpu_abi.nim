@@ -36,5 +36,8 @@ proc blsgpu_hash_to_g2*(ctx: BlsGpuCtx, msgs: ptr byte, n, msgLen: csize_t, dst:
 proc blsgpu_aggregate_g1*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: pointer): cint
 proc blsgpu_aggregate_g2*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: pointer): cint
 proc blsgpu_msm_g1*(ctx: BlsGpuCtx, points, scalars: pointer, n, nbits: csize_t, dst: pointer): cint
+proc blsgpu_msm_g2*(ctx: BlsGpuCtx, points, scalars: pointer, n, nbits: csize_t, dst: pointer): cint
+proc blsgpu_combine*(ctx: BlsGpuCtx, srb: ptr array[32, byte], pubkeys, sigs: pointer, n: csize_t,
+                     pkOut, sigOut: pointer): cint
 {.pop.}
 {.pop.}

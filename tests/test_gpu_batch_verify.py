@@ -137,3 +137,23 @@ def test_device_generated_sets_verify(cache, br, srb):
     bad = bytearray(sets)
     bad[5 * 320 + 96] ^= 1                                                        # flip one message bit
     assert both(cache, br, bytes(bad), srb, 4) is False
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 100, 1000])
+def test_combine_same_message(cache, br, srb, n):
+    """MultiSignatureSet.combine (tests/t_batch_verifier.nim:159-177): same scalars, same Pippenger results as BLST,
+    and the combined set verifies like the reference's."""
+    import nim_blscurve_b200 as bg
+    sets = [br.make_set(i, b"same message") for i in range(n)]   # (pk, SHA256(text), sig) on one message
+    msg = sets[0][96:128]
+    pks = [s[:96] for s in sets]
+    sigs = [s[128:320] for s in sets]
+    pk, sig = bg.combine(cache, srb, pks, sigs)
+    assert (pk, sig) == br.combine(srb, b"".join(pks), b"".join(sigs))
+    ms = bg.MultiSignatureSet(pks, msg, sigs)
+    one = ms.combine(cache, srb)
+    assert bg.batchVerifySerial(cache, [one], srb) == br.batch_verify(one.to_bytes(), srb, 0)[0] is True
+    # a shuffled signature list must fail (t_batch_verifier.nim:171-177)
+    if n >= 2:
+        bad = bg.MultiSignatureSet(pks, msg, sigs[1:] + sigs[:1]).combine(cache, srb)
+        assert bg.batchVerifySerial(cache, [bad], srb) is False
