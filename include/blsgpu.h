@@ -107,6 +107,42 @@ int blsgpu_hash_to_g2(blsgpu_ctx *ctx, const uint8_t *msgs, size_t n, size_t msg
 int blsgpu_aggregate_g1(blsgpu_ctx *ctx, const void *points96, size_t n, uint8_t out96[96]);
 int blsgpu_aggregate_g2(blsgpu_ctx *ctx, const void *points192, size_t n, uint8_t out192[192]);
 
+/* Segmented aggregateAll: segment k sums points[offsets[k] .. offsets[k+1]) (an empty segment yields infinity, the case
+ * aggregateAll reports as false, blst_min_pubkey_sig_core.nim:183-184); out96 receives nseg affine points.  One launch for
+ * all committees of a block (128 x 128 + 512 public keys). */
+int blsgpu_aggregate_g1_segments(blsgpu_ctx *ctx, const void *points96, const uint32_t *offsets, size_t nseg,
+                                 uint8_t *out96);
+
+/* aggregateVerify (blscurve/bls_sig_min_pubkey.nim:155-204 over ContextCoreAggregateVerify,
+ * blst_min_pubkey_sig_core.nim:310-398: update per pair, finish(signature), commit, finalverify): n (public key, message)
+ * pairs and ONE signature, no blinding: FE( prod ML(pk_i, H(m_i)) * ML(sig, -G1) ) == 1.  Message i is
+ * msgs[msg_offsets[i] .. msg_offsets[i+1]); dst as in blsgpu_hash_to_g2.  n == 0 -> 0; an infinite public key -> 0
+ * (aggregate.c:296); an infinite signature contributes nothing (aggregate.c:486-492).  With n == 1 this is `verify` /
+ * coreVerifyNoGroupCheck (blst_min_pubkey_sig_core.nim:264-297).  gt_out (nullable): the 576 GT bytes. */
+int blsgpu_aggregate_verify(blsgpu_ctx *ctx, const void *pubkeys96, size_t n, const uint8_t *msgs,
+                            const uint32_t *msg_offsets, const uint8_t *dst, size_t dst_len, const void *sig192,
+                            uint8_t gt_out[576]);
+
+/* fastAggregateVerify (bls_sig_min_pubkey.nim:238-258): aggregateAll of the n public keys on the device, then the
+ * single-pair check above on one message.  n == 0 -> 0. */
+int blsgpu_fast_aggregate_verify(blsgpu_ctx *ctx, const void *pubkeys96, size_t n, const uint8_t *msg, size_t msg_len,
+                                 const uint8_t *dst, size_t dst_len, const void *sig192, uint8_t gt_out[576]);
+
+/* Batched PublicKey.fromBytes / Signature.fromBytes (blscurve/blst/bls_sig_io.nim:42-122): n encodings of in_len bytes
+ * each (public keys: 48 compressed -> blst_p1_uncompress e1.c:261, or 96 -> blst_p1_deserialize e1.c:328; signatures: 96
+ * -> blst_p2_uncompress e2.c:312, or 192 -> blst_p2_deserialize e2.c:391), then "infinity public keys are not allowed"
+ * and, when group_check != 0, the subgroup check (blst_p1_affine_in_g1 / blst_p2_affine_in_g2); group_check == 0 is
+ * fromBytesKnownOnCurve.  out receives n affine points in the in-memory Montgomery layout (all-zero on failure),
+ * status[i] (nullable) the BLST_ERROR of element i (bindings/blst.h:47-56: 0 success, 1 bad encoding, 2 not on curve,
+ * 3 not in group, 6 public key is infinity).  Returns 1 when every element decoded, 0 otherwise, < 0 on runtime error. */
+int blsgpu_pubkeys_from_bytes(blsgpu_ctx *ctx, const uint8_t *in, size_t n, size_t in_len, int group_check,
+                              uint8_t *out96, uint8_t *status);
+int blsgpu_signatures_from_bytes(blsgpu_ctx *ctx, const uint8_t *in, size_t n, size_t in_len, int group_check,
+                                 uint8_t *out192, uint8_t *status);
+/* The inverse (blst_p1_affine_compress / blst_p2_affine_compress, bls_sig_io.nim:20-36): n x 48 / n x 96 bytes. */
+int blsgpu_pubkeys_to_bytes(blsgpu_ctx *ctx, const void *points96, size_t n, uint8_t *out48);
+int blsgpu_signatures_to_bytes(blsgpu_ctx *ctx, const void *points192, size_t n, uint8_t *out96);
+
 /* G1 multi-scalar multiplication (replaces blst_p1s_mult_pippenger + blst_p1_to_affine,
  * vendor/blst/src/multi_scalar.c:415-434; call shape of benchmarks/bls12381_msm_g1.nim:57-59):
  * points n x 96 bytes affine, scalars n x ceil(nbits/8) bytes little-endian, out = affine sum. */

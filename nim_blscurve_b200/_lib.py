@@ -15,6 +15,8 @@ SYMBOLS = [
     "blsgpu_set_stream", "blsgpu_rlc_scalars", "blsgpu_batch_verify", "blsgpu_batch_verify_dev",
     "blsgpu_partial", "blsgpu_partial_dev", "blsgpu_finalize", "blsgpu_finalize_dev", "blsgpu_hash_to_g2", "blsgpu_aggregate_g1", "blsgpu_aggregate_g2",
     "blsgpu_msm_g1", "blsgpu_msm_g1_dev", "blsgpu_msm_g2", "blsgpu_msm_g2_dev", "blsgpu_combine", "blsgpu_last_stage_ms", "blsgpu_stage_name", "blsgpu_last_launches",
+    "blsgpu_aggregate_g1_segments", "blsgpu_aggregate_verify", "blsgpu_fast_aggregate_verify",
+    "blsgpu_pubkeys_from_bytes", "blsgpu_signatures_from_bytes", "blsgpu_pubkeys_to_bytes", "blsgpu_signatures_to_bytes",
     "blsgpu_test_fp", "blsgpu_imad_peak", "blsgpu_fpmul_peak", "blsgpu_make_sets", "blsgpu_msm_make_inputs",
 ]
 
@@ -58,6 +60,13 @@ def lib():
     L.blsgpu_msm_g2.argtypes = [vp, vp, vp, sz, sz, vp]
     L.blsgpu_msm_g2_dev.argtypes = [vp, vp, vp, sz, sz, vp]
     L.blsgpu_combine.argtypes = [vp, u8p, vp, vp, sz, vp, vp]
+    L.blsgpu_aggregate_g1_segments.argtypes = [vp, vp, vp, sz, vp]
+    L.blsgpu_aggregate_verify.argtypes = [vp, vp, sz, vp, vp, vp, sz, vp, vp]
+    L.blsgpu_fast_aggregate_verify.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp]
+    L.blsgpu_pubkeys_from_bytes.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp]
+    L.blsgpu_signatures_from_bytes.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp]
+    L.blsgpu_pubkeys_to_bytes.argtypes = [vp, vp, sz, vp]
+    L.blsgpu_signatures_to_bytes.argtypes = [vp, vp, sz, vp]
     L.blsgpu_last_stage_ms.argtypes = [vp, vp, C.c_int]
     L.blsgpu_stage_name.restype = C.c_char_p
     L.blsgpu_stage_name.argtypes = [C.c_int]

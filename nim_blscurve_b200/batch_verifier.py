@@ -219,3 +219,95 @@ def rlcScalars(cache: BatchedBLSVerifierCache, srb: bytes, n: int, chunks: int):
     if rc < 0:
         raise BlsGpuError(f"rlc_scalars failed ({rc}): {cache.last_error()}")
     return list(out)
+
+
+# ---- blscurve/bls_sig_min_pubkey.nim: aggregateVerify :155-204, fastAggregateVerify :238-258, verify :108-125 ----
+DST = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_"          # bls_sig_min_pubkey.nim:31
+
+
+def _check(rc, what, cache):
+    if rc < 0:
+        raise BlsGpuError(f"{what} failed ({rc}): {cache.last_error()}")
+    return bool(rc)
+
+
+def aggregateVerify(cache: BatchedBLSVerifierCache, publicKeys: Sequence[bytes], messages: Sequence[bytes],
+                    signature: bytes, dst: bytes = DST, want_gt: bool = False):
+    """One signature over n (public key, message) pairs; False on length mismatch or n == 0 (:164-169)."""
+    if len(publicKeys) != len(messages) or len(publicKeys) < 1:
+        return (False, bytes(576)) if want_gt else False
+    offs, o = [0], 0
+    for m in messages:
+        o += len(m)
+        offs.append(o)
+    gt = (C.c_uint8 * 576)()
+    rc = lib().blsgpu_aggregate_verify(cache.handle, b"".join(publicKeys), len(publicKeys), b"".join(messages) or None,
+                                       (C.c_uint32 * len(offs))(*offs), dst, len(dst), signature, gt)
+    ok = _check(rc, "aggregate_verify", cache)
+    return (ok, bytes(gt)) if want_gt else ok
+
+
+def verify(cache: BatchedBLSVerifierCache, publicKey: bytes, message: bytes, signature: bytes, dst: bytes = DST) -> bool:
+    """coreVerifyNoGroupCheck (blst_min_pubkey_sig_core.nim:264-297) = the one-pair case."""
+    return aggregateVerify(cache, [publicKey], [message], signature, dst)
+
+
+def fastAggregateVerify(cache: BatchedBLSVerifierCache, publicKeys: Sequence[bytes], message: bytes, signature: bytes,
+                        dst: bytes = DST, want_gt: bool = False):
+    """aggregateAll(publicKeys) on the device, then verify; False on an empty key list (:251-253)."""
+    if len(publicKeys) == 0:
+        return (False, bytes(576)) if want_gt else False
+    gt = (C.c_uint8 * 576)()
+    rc = lib().blsgpu_fast_aggregate_verify(cache.handle, b"".join(publicKeys), len(publicKeys), message or None,
+                                            len(message), dst, len(dst), signature, gt)
+    ok = _check(rc, "fast_aggregate_verify", cache)
+    return (ok, bytes(gt)) if want_gt else ok
+
+
+def aggregateAllSegments(cache: BatchedBLSVerifierCache, groups: Sequence[Sequence[bytes]]):
+    """aggregateAll for many committees in one launch -> [(ok, 96-byte point)], ok False for an empty committee."""
+    offs, o, flat = [0], 0, []
+    for g in groups:
+        o += len(g)
+        offs.append(o)
+        flat.extend(g)
+    if not groups:
+        return []
+    out = (C.c_uint8 * (96 * len(groups)))()
+    rc = lib().blsgpu_aggregate_g1_segments(cache.handle, b"".join(flat) or None, (C.c_uint32 * len(offs))(*offs),
+                                            len(groups), out)
+    _check(rc, "aggregate_g1_segments", cache)
+    raw = bytes(out)
+    return [(len(g) > 0, raw[96 * i:96 * i + 96]) for i, g in enumerate(groups)]
+
+
+# ---- blscurve/blst/bls_sig_io.nim:42-122: fromBytes / fromBytesKnownOnCurve, batched ----
+def publicKeysFromBytes(cache: BatchedBLSVerifierCache, raw: bytes, size: int = 48, group_check: bool = True):
+    """n encodings of `size` (48 or 96) bytes -> (points n*96, [BLST_ERROR per element]); element ok iff status 0."""
+    n = len(raw) // size
+    out, st = (C.c_uint8 * (96 * n))(), (C.c_uint8 * n)()
+    _check(lib().blsgpu_pubkeys_from_bytes(cache.handle, raw, n, size, 1 if group_check else 0, out, st),
+           "pubkeys_from_bytes", cache)
+    return bytes(out), list(st)
+
+
+def signaturesFromBytes(cache: BatchedBLSVerifierCache, raw: bytes, size: int = 96, group_check: bool = True):
+    n = len(raw) // size
+    out, st = (C.c_uint8 * (192 * n))(), (C.c_uint8 * n)()
+    _check(lib().blsgpu_signatures_from_bytes(cache.handle, raw, n, size, 1 if group_check else 0, out, st),
+           "signatures_from_bytes", cache)
+    return bytes(out), list(st)
+
+
+def publicKeysToBytes(cache: BatchedBLSVerifierCache, points96: bytes) -> bytes:
+    n = len(points96) // 96
+    out = (C.c_uint8 * (48 * n))()
+    _check(lib().blsgpu_pubkeys_to_bytes(cache.handle, points96, n, out), "pubkeys_to_bytes", cache)
+    return bytes(out)
+
+
+def signaturesToBytes(cache: BatchedBLSVerifierCache, points192: bytes) -> bytes:
+    n = len(points192) // 192
+    out = (C.c_uint8 * (96 * n))()
+    _check(lib().blsgpu_signatures_to_bytes(cache.handle, points192, n, out), "signatures_to_bytes", cache)
+    return bytes(out)

@@ -278,63 +278,11 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
     if (nseg > 63) nseg = 63;
 }
 
-// all per-set stages + reductions; leaves the rank partial in d_partials[slot]
-static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t first, size_t total_n,
-                       const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, int slot) {
+// Multi-Miller loop over the np pairs (d_Q[i], d_P[i]) + reductions; leaves conj(prod ML) in d_partials[slot]
+static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
     cudaStream_t s = ctx->stream;
-    ctx->launches = 0;
-    CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
-    BEGIN(ST_SCALARS, s);
-    int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars);
-    if (rc) return rc;
-    END(ST_SCALARS, s);
-    // fork: the signature-side sum only needs the scalars; it is latency-bound (bucket reduction, Horner) and hides
-    // behind the per-set stages on a second stream, joined before the Miller-loop lines
-    cudaStream_t g = ctx->use_side ? ctx->side : s;
-    if (ctx->use_side) {
-        CK(cudaEventRecord(ctx->ev[EV_FORK], s));
-        CK(cudaStreamWaitEvent(g, ctx->ev[EV_FORK], 0));
-    }
-    BEGIN(ST_G2MUL, g);
-    // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
-    // buckets, n independent 64-bit multiplications + tree below that
-    static const size_t g2_msm_min = getenv("BLSGPU_G2_MSM_MIN") ? (size_t)atoll(getenv("BLSGPU_G2_MSM_MIN")) : 2048;
-    if (n >= g2_msm_min) {
-        std::string err;
-        rc = msm_run<fp2>(ctx->msm, (const uint8_t *)d_sets + offsetof(sigset, sig), sizeof(sigset), (const uint8_t *)ctx->d_r, 8,
-                          n, 64, g, ctx->d_S, nullptr, &ctx->launches, err);
-        if (rc) return fail(ctx, rc == -1 ? BLSGPU_ERR_CUDA : BLSGPU_ERR_ARG, err.c_str());
-        END(ST_G2MUL, g);
-        BEGIN(ST_G2SUM, g);
-    } else {
-        k_g2_mul<<<nblk(n), 128, 0, g>>>(d_sets, ctx->d_r, n, ctx->d_S);
-        ctx->launches++;
-        END(ST_G2MUL, g);
-        BEGIN(ST_G2SUM, g);
-        for (size_t m = n; m > 1;) {
-            size_t half = (m + 1) / 2;
-            k_g2_tree<<<nblk(half), 128, 0, g>>>(ctx->d_S, m, half);
-            ctx->launches++;
-            m = half;
-        }
-    }
-    k_sig_pair<<<1, 32, 0, g>>>(ctx->d_S, n, ctx->d_Q, ctx->d_P);
-    ctx->launches++;
-    END(ST_G2SUM, g);
-    if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_JOIN], g));
-    BEGIN(ST_HASH, s);
-    k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
-    END(ST_HASH, s);
-    BEGIN(ST_G1MUL, s);
-    k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
-    END(ST_G1MUL, s);
-    BEGIN(ST_AFFINE, s);
-    k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P);
-    END(ST_AFFINE, s);
-    ctx->launches += 3;
-    if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));   // join: pair number n is in place
-    // Miller loop over n + 1 pairs, tile by tile: lines, then per-(group, segment) accumulation
-    const size_t np = n + 1;
+    int rc;
+    // tile by tile: lines, then per-(group, segment) accumulation
     const bool team = ctx->acc_team;
     int G, nseg;
     miller_shape(np < ctx->lines_cap ? np : ctx->lines_cap, team, G, nseg);
@@ -394,6 +342,64 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     END(ST_PARTIAL, s);
     CK(cudaGetLastError());
     return 0;
+}
+
+// all per-set stages + reductions; leaves the rank partial in d_partials[slot]
+static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t first, size_t total_n,
+                       const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, int slot) {
+    cudaStream_t s = ctx->stream;
+    ctx->launches = 0;
+    CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
+    BEGIN(ST_SCALARS, s);
+    int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars);
+    if (rc) return rc;
+    END(ST_SCALARS, s);
+    // fork: the signature-side sum only needs the scalars; it is latency-bound (bucket reduction, Horner) and hides
+    // behind the per-set stages on a second stream, joined before the Miller-loop lines
+    cudaStream_t g = ctx->use_side ? ctx->side : s;
+    if (ctx->use_side) {
+        CK(cudaEventRecord(ctx->ev[EV_FORK], s));
+        CK(cudaStreamWaitEvent(g, ctx->ev[EV_FORK], 0));
+    }
+    BEGIN(ST_G2MUL, g);
+    // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
+    // buckets, n independent 64-bit multiplications + tree below that
+    static const size_t g2_msm_min = getenv("BLSGPU_G2_MSM_MIN") ? (size_t)atoll(getenv("BLSGPU_G2_MSM_MIN")) : 2048;
+    if (n >= g2_msm_min) {
+        std::string err;
+        rc = msm_run<fp2>(ctx->msm, (const uint8_t *)d_sets + offsetof(sigset, sig), sizeof(sigset), (const uint8_t *)ctx->d_r, 8,
+                          n, 64, g, ctx->d_S, nullptr, &ctx->launches, err);
+        if (rc) return fail(ctx, rc == -1 ? BLSGPU_ERR_CUDA : BLSGPU_ERR_ARG, err.c_str());
+        END(ST_G2MUL, g);
+        BEGIN(ST_G2SUM, g);
+    } else {
+        k_g2_mul<<<nblk(n), 128, 0, g>>>(d_sets, ctx->d_r, n, ctx->d_S);
+        ctx->launches++;
+        END(ST_G2MUL, g);
+        BEGIN(ST_G2SUM, g);
+        for (size_t m = n; m > 1;) {
+            size_t half = (m + 1) / 2;
+            k_g2_tree<<<nblk(half), 128, 0, g>>>(ctx->d_S, m, half);
+            ctx->launches++;
+            m = half;
+        }
+    }
+    k_sig_pair<<<1, 32, 0, g>>>(ctx->d_S, n, ctx->d_Q, ctx->d_P);
+    ctx->launches++;
+    END(ST_G2SUM, g);
+    if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_JOIN], g));
+    BEGIN(ST_HASH, s);
+    k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+    END(ST_HASH, s);
+    BEGIN(ST_G1MUL, s);
+    k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
+    END(ST_G1MUL, s);
+    BEGIN(ST_AFFINE, s);
+    k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P);
+    END(ST_AFFINE, s);
+    ctx->launches += 3;
+    if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));   // join: pair number n is in place
+    return run_miller(ctx, n + 1, slot);
 }
 
 static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_inf, const fp12 *d_partials = nullptr,
@@ -573,7 +579,7 @@ extern "C" int blsgpu_hash_to_g2(blsgpu_ctx *ctx, const uint8_t *msgs, size_t n,
     uint8_t *base = (uint8_t *)ctx->d_misc;
     if (msg_len) CK(cudaMemcpyAsync(base + o_msgs, msgs, n * msg_len, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(base + o_dst, dst, dst_len, cudaMemcpyHostToDevice, s));
-    k_hash_to_g2<<<nblk(n), 128, 0, s>>>(base + o_msgs, n, msg_len, base + o_dst, (uint32_t)dst_len,
+    k_hash_to_g2<<<nblk(n), 128, 0, s>>>(base + o_msgs, n, msg_len, nullptr, base + o_dst, (uint32_t)dst_len,
                                          out_affine ? (g2_aff *)(base + o_aff) : nullptr, out_compressed ? base + o_comp : nullptr);
     CK(cudaGetLastError());
     if (out_affine) CK(cudaMemcpyAsync(out_affine, base + o_aff, n * 192, cudaMemcpyDeviceToHost, s));
@@ -620,6 +626,196 @@ extern "C" int blsgpu_aggregate_g2(blsgpu_ctx *ctx, const void *points192, size_
     CK(cudaMemcpyAsync(out192, A, 192, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return 1;
+}
+
+// ---- aggregateVerify / fastAggregateVerify on the device ----
+// d_pks: n affine public keys on the device; messages/DST/signature are staged into d_misc by the callers below.
+static int verify_pairs_dev(blsgpu_ctx *ctx, const g1_aff *d_pks, size_t n, const uint8_t *d_msgs, const uint32_t *d_offs,
+                            const uint8_t *d_dst, size_t dst_len, const g2_aff *d_sig, uint8_t gt_out[576]) {
+    cudaStream_t s = ctx->stream;
+    ctx->launches = 0;
+    CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
+    BEGIN(ST_HASH, s);
+    k_hash_to_g2<<<nblk(n), 128, 0, s>>>(d_msgs, n, 0, d_offs, d_dst, (uint32_t)dst_len, ctx->d_Q, nullptr);
+    END(ST_HASH, s);
+    k_verify_pairs<<<nblk(n + 1), 128, 0, s>>>(d_pks, n, d_sig, ctx->d_Q, ctx->d_P, ctx->d_flags);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    int rc = run_miller(ctx, n + 1, 0);
+    if (rc) return rc;
+    int pk_inf = 0;
+    rc = run_final(ctx, 1, gt_out, &pk_inf);
+    if (rc < 0) return rc;
+    if (pk_inf) { if (gt_out) memset(gt_out, 0, 576); return 0; }
+    return rc;
+}
+
+// host staging layout in d_misc: [msgs | offsets | dst | sig | pks]; returns device pointers
+struct verify_stage { uint8_t *msgs; uint32_t *offs; uint8_t *dst; g2_aff *sig; g1_aff *pks; };
+static int stage_verify_inputs(blsgpu_ctx *ctx, const void *pks, size_t npk, const uint8_t *msgs, size_t msg_bytes,
+                               const uint32_t *offs, size_t noffs, const uint8_t *dst, size_t dst_len, const void *sig,
+                               size_t extra, verify_stage &st, uint8_t **extra_ptr) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o_msgs = 0, o_offs = up(msg_bytes + 1), o_dst = o_offs + up(noffs * 4), o_sig = o_dst + up(dst_len + 1),
+           o_pks = o_sig + 256, o_extra = o_pks + up(npk * 96), total = o_extra + up(extra);
+    int rc = ensure_misc(ctx, total);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    cudaStream_t s = ctx->stream;
+    st.msgs = base + o_msgs; st.offs = (uint32_t *)(base + o_offs); st.dst = base + o_dst;
+    st.sig = (g2_aff *)(base + o_sig); st.pks = (g1_aff *)(base + o_pks);
+    if (extra_ptr) *extra_ptr = base + o_extra;
+    if (msg_bytes) CK(cudaMemcpyAsync(st.msgs, msgs, msg_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(st.offs, offs, noffs * 4, cudaMemcpyHostToDevice, s));
+    if (dst_len) CK(cudaMemcpyAsync(st.dst, dst, dst_len, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(st.sig, sig, 192, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(st.pks, pks, npk * 96, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+extern "C" int blsgpu_aggregate_verify(blsgpu_ctx *ctx, const void *pubkeys96, size_t n, const uint8_t *msgs,
+                                       const uint32_t *msg_offsets, const uint8_t *dst, size_t dst_len, const void *sig192,
+                                       uint8_t gt_out[576]) {
+    if (!ctx) return BLSGPU_ERR_ARG;
+    if (gt_out) memset(gt_out, 0, 576);
+    if (n == 0) return 0;                                   // bls_sig_min_pubkey.nim:140, :167, :189
+    if (!pubkeys96 || !msg_offsets || !sig192 || (!dst && dst_len)) return fail(ctx, BLSGPU_ERR_ARG, "NULL argument");
+    if (dst_len > 255) return fail(ctx, BLSGPU_ERR_ARG, "DST longer than 255 bytes is not supported");
+    if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "more pairs than the context capacity");
+    for (size_t i = 0; i < n; i++)
+        if (msg_offsets[i + 1] < msg_offsets[i]) return fail(ctx, BLSGPU_ERR_ARG, "message offsets must be non-decreasing");
+    if (msg_offsets[n] && !msgs) return fail(ctx, BLSGPU_ERR_ARG, "msgs is NULL");
+    CK(cudaSetDevice(ctx->device));
+    verify_stage st;
+    int rc = stage_verify_inputs(ctx, pubkeys96, n, msgs, msg_offsets[n], msg_offsets, n + 1, dst, dst_len, sig192, 0, st, nullptr);
+    if (rc) return rc;
+    rc = verify_pairs_dev(ctx, st.pks, n, st.msgs, st.offs, st.dst, dst_len, st.sig, gt_out);
+    collect_stage_times(ctx, true);
+    return rc;
+}
+
+extern "C" int blsgpu_fast_aggregate_verify(blsgpu_ctx *ctx, const void *pubkeys96, size_t n, const uint8_t *msg,
+                                            size_t msg_len, const uint8_t *dst, size_t dst_len, const void *sig192,
+                                            uint8_t gt_out[576]) {
+    if (!ctx) return BLSGPU_ERR_ARG;
+    if (gt_out) memset(gt_out, 0, 576);
+    if (n == 0) return 0;                                   // bls_sig_min_pubkey.nim:251-253
+    if (!pubkeys96 || !sig192 || (!msg && msg_len) || (!dst && dst_len)) return fail(ctx, BLSGPU_ERR_ARG, "NULL argument");
+    if (dst_len > 255) return fail(ctx, BLSGPU_ERR_ARG, "DST longer than 255 bytes is not supported");
+    if (msg_len > 0xffffffffu || n > 0xffffffffu) return fail(ctx, BLSGPU_ERR_ARG, "input too large");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t offs[4] = {0, (uint32_t)msg_len, 0, (uint32_t)n};       // message offsets | key-segment offsets
+    verify_stage st;
+    uint8_t *extra = nullptr;
+    int rc = stage_verify_inputs(ctx, pubkeys96, n, msg, msg_len, offs, 4, dst, dst_len, sig192, 512, st, &extra);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    g1_jac *aggj = (g1_jac *)extra;
+    g1_aff *agg = (g1_aff *)(extra + 256);
+    k_g1_seg_sum<<<1, 128, 0, s>>>(st.pks, st.offs + 2, 1, aggj);      // aggregateAll (blst_min_pubkey_sig_core.nim:179)
+    k_g1_to_affine_many<<<1, 128, 0, s>>>(aggj, 1, agg);
+    CK(cudaGetLastError());
+    rc = verify_pairs_dev(ctx, agg, 1, st.msgs, st.offs, st.dst, dst_len, st.sig, gt_out);
+    ctx->launches += 2;
+    collect_stage_times(ctx, true);
+    return rc;
+}
+
+extern "C" int blsgpu_aggregate_g1_segments(blsgpu_ctx *ctx, const void *points96, const uint32_t *offsets, size_t nseg,
+                                            uint8_t *out96) {
+    if (!ctx || !offsets || !out96) return BLSGPU_ERR_ARG;
+    if (nseg == 0) return 0;
+    for (size_t i = 0; i < nseg; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, BLSGPU_ERR_ARG, "segment offsets must be non-decreasing");
+    const size_t n = offsets[nseg];
+    if (n && !points96) return BLSGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o_pts = 0, o_offs = up(n * 96 + 1), o_j = o_offs + up((nseg + 1) * 4), o_a = o_j + up(nseg * sizeof(g1_jac));
+    int rc = ensure_misc(ctx, o_a + up(nseg * 96));
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    if (n) CK(cudaMemcpyAsync(base + o_pts, points96, n * 96, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(base + o_offs, offsets, (nseg + 1) * 4, cudaMemcpyHostToDevice, s));
+    k_g1_seg_sum<<<nblk(nseg, 4), 128, 0, s>>>((const g1_aff *)(base + o_pts), (const uint32_t *)(base + o_offs), nseg,
+                                               (g1_jac *)(base + o_j));
+    k_g1_to_affine_many<<<nblk(nseg), 128, 0, s>>>((const g1_jac *)(base + o_j), nseg, (g1_aff *)(base + o_a));
+    ctx->launches = 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out96, base + o_a, nseg * 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 1;
+}
+
+// ---- batched fromBytes with checks ----
+template <int G2>
+static int from_bytes_api(blsgpu_ctx *ctx, const uint8_t *in, size_t n, size_t in_len, int group_check, uint8_t *out,
+                          uint8_t *status) {
+    const size_t pb = G2 ? 192 : 96, clen = G2 ? 96 : 48;
+    if (!ctx || !out) return BLSGPU_ERR_ARG;
+    if (n == 0) return 1;
+    if (!in) return BLSGPU_ERR_ARG;
+    if (in_len != clen && in_len != pb) return fail(ctx, BLSGPU_ERR_ARG, "encoded length must be the compressed or the serialized size");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o_in = 0, o_out = up(n * in_len), o_st = o_out + up(n * pb), o_cnt = o_st + up(n);
+    int rc = ensure_misc(ctx, o_cnt + 256);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    CK(cudaMemcpyAsync(base + o_in, in, n * in_len, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(base + o_cnt, 0, 4, s));
+    if (G2) k_signatures_from_bytes<<<nblk(n), 128, 0, s>>>(base + o_in, n, (int)in_len, group_check, (g2_aff *)(base + o_out),
+                                                            base + o_st, (int *)(base + o_cnt));
+    else k_pubkeys_from_bytes<<<nblk(n), 128, 0, s>>>(base + o_in, n, (int)in_len, group_check, (g1_aff *)(base + o_out),
+                                                      base + o_st, (int *)(base + o_cnt));
+    ctx->launches = 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, base + o_out, n * pb, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, base + o_st, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_pinned, base + o_cnt, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int nfail;
+    memcpy(&nfail, ctx->h_pinned, 4);
+    return nfail == 0 ? 1 : 0;
+}
+
+extern "C" int blsgpu_pubkeys_from_bytes(blsgpu_ctx *ctx, const uint8_t *in, size_t n, size_t in_len, int group_check,
+                                         uint8_t *out96, uint8_t *status) {
+    return from_bytes_api<0>(ctx, in, n, in_len, group_check, out96, status);
+}
+extern "C" int blsgpu_signatures_from_bytes(blsgpu_ctx *ctx, const uint8_t *in, size_t n, size_t in_len, int group_check,
+                                            uint8_t *out192, uint8_t *status) {
+    return from_bytes_api<1>(ctx, in, n, in_len, group_check, out192, status);
+}
+
+template <int G2>
+static int compress_api(blsgpu_ctx *ctx, const void *points, size_t n, uint8_t *out) {
+    const size_t pb = G2 ? 192 : 96, clen = G2 ? 96 : 48;
+    if (!ctx || !out) return BLSGPU_ERR_ARG;
+    if (n == 0) return 1;
+    if (!points) return BLSGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    size_t o_out = (n * pb + 255) & ~(size_t)255;
+    int rc = ensure_misc(ctx, o_out + n * clen + 256);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    CK(cudaMemcpyAsync(base, points, n * pb, cudaMemcpyHostToDevice, s));
+    if (G2) k_g2_compress<<<nblk(n), 128, 0, s>>>((const g2_aff *)base, n, base + o_out);
+    else k_g1_compress<<<nblk(n), 128, 0, s>>>((const g1_aff *)base, n, base + o_out);
+    ctx->launches = 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, base + o_out, n * clen, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 1;
+}
+extern "C" int blsgpu_pubkeys_to_bytes(blsgpu_ctx *ctx, const void *points96, size_t n, uint8_t *out48) {
+    return compress_api<0>(ctx, points96, n, out48);
+}
+extern "C" int blsgpu_signatures_to_bytes(blsgpu_ctx *ctx, const void *points192, size_t n, uint8_t *out96) {
+    return compress_api<1>(ctx, points192, n, out96);
 }
 
 template <class F>

@@ -16,6 +16,7 @@
 #include "h2c.cuh"
 #include "pairing.cuh"
 #include "acc_team.cuh"
+#include "io.cuh"
 
 namespace bls {
 
@@ -480,16 +481,108 @@ __global__ void k_final(const fp12 *partials, int count, const int *flags, uint8
 }
 
 // ---- generic hash_to_G2 entry (arbitrary message length and DST, both in global memory) ----
-__global__ void BLS_LB k_hash_to_g2(const uint8_t *msgs, size_t n, size_t msg_len, const uint8_t *dst,
-                                                    uint32_t dst_len, g2_aff *out_aff, uint8_t *out_comp) {
+// message i is msgs[offs[i] .. offs[i+1]) when offs is given, else msgs[i*msg_len .. (i+1)*msg_len)
+__global__ void BLS_LB k_hash_to_g2(const uint8_t *msgs, size_t n, size_t msg_len, const uint32_t *offs, const uint8_t *dst,
+                                    uint32_t dst_len, g2_aff *out_aff, uint8_t *out_comp) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_jac h;
-    hash_to_g2_jac(h, msgs + i * msg_len, msg_len, dst, dst_len);
+    if (offs) hash_to_g2_jac(h, msgs + offs[i], offs[i + 1] - offs[i], dst, dst_len);
+    else hash_to_g2_jac(h, msgs + i * msg_len, msg_len, dst, dst_len);
     g2_aff a;
     pt_to_affine(a, h);
     if (out_aff) out_aff[i] = a;
     if (out_comp) g2_compress(out_comp + 96 * i, a);
+}
+
+// ---- aggregateVerify / fastAggregateVerify (bls_sig_min_pubkey.nim:127-273) ----
+// Pairs for the un-blinded check  FE( prod ML(pk_i, H(m_i)) * ML(sig, -G1) ) == 1: P[i] = pk_i (an infinite public key
+// fails the call, aggregate.c:296), pair n = (sig, -G1); an infinite signature yields neutral lines (aggregate.c:486-492).
+__global__ void k_verify_pairs(const g1_aff *pks, size_t n, const g2_aff *sig, g2_aff *Q, g1_aff *P, int *flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        g1_aff pk = pks[i];
+        if (aff_is_inf(pk)) atomicOr(flags, 1);
+        P[i] = pk;
+    } else if (i == n) {
+        Q[n] = *sig;
+        g1_aff g;
+        g.x = G1_GEN_X;
+        fp_neg(g.y, G1_GEN_Y);
+        P[n] = g;
+    }
+}
+
+// Segmented aggregateAll (blst_min_pubkey_sig_core.nim:179-195 once per segment): one warp per segment, every lane
+// sums a strided slice with mixed additions, then a shared-memory tree over the 32 partial sums.
+__global__ void __launch_bounds__(128) k_g1_seg_sum(const g1_aff *pts, const uint32_t *offs, size_t nseg, g1_jac *out) {
+    __shared__ g1_jac sm[4][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t sgm = (size_t)blockIdx.x * 4 + warp;
+    if (sgm >= nseg) return;                               // whole warp leaves together
+    const uint32_t lo = offs[sgm], hi = offs[sgm + 1];
+    g1_jac acc;
+    pt_set_inf(acc);
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
+        g1_aff a = pts[i];
+        pt_add_affine(acc, acc, a);
+    }
+    for (int half = 16; half >= 1; half >>= 1) {
+        if (lane >= half && lane < 2 * half) sm[warp][lane - half] = acc;
+        __syncwarp();
+        if (lane < half) {
+            g1_jac b = sm[warp][lane];
+            pt_add(acc, acc, b);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) out[sgm] = acc;
+}
+__global__ void BLS_LB k_g1_to_affine_many(const g1_jac *in, size_t n, g1_aff *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_jac j = in[i];
+    g1_aff a;
+    pt_to_affine(a, j);
+    out[i] = a;
+}
+
+// ---- batched fromBytes with checks (io.cuh) ----
+__global__ void BLS_LB k_pubkeys_from_bytes(const uint8_t *in, size_t n, int len, int group_check, g1_aff *out,
+                                            uint8_t *status, int *nfail) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t raw[96];
+    for (int k = 0; k < len; k++) raw[k] = in[i * len + k];
+    g1_aff p;
+    int err = pubkey_from_bytes(p, raw, len, group_check != 0);
+    out[i] = p;
+    status[i] = (uint8_t)err;
+    if (err) atomicAdd(nfail, 1);
+}
+__global__ void BLS_LB k_signatures_from_bytes(const uint8_t *in, size_t n, int len, int group_check, g2_aff *out,
+                                               uint8_t *status, int *nfail) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t raw[192];
+    for (int k = 0; k < len; k++) raw[k] = in[i * len + k];
+    g2_aff p;
+    int err = signature_from_bytes(p, raw, len, group_check != 0);
+    out[i] = p;
+    status[i] = (uint8_t)err;
+    if (err) atomicAdd(nfail, 1);
+}
+__global__ void k_g1_compress(const g1_aff *in, size_t n, uint8_t *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_aff a = in[i];
+    g1_compress(out + 48 * i, a);
+}
+__global__ void k_g2_compress(const g2_aff *in, size_t n, uint8_t *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_aff a = in[i];
+    g2_compress(out + 96 * i, a);
 }
 
 // ---- aggregateAll helpers ----

@@ -43,6 +43,18 @@ void blst_p2_add_or_double_affine(blst_p2 *out, const blst_p2 *a, const blst_p2_
 void blst_p2_mult(blst_p2 *out, const blst_p2 *p, const uint8_t *scalar, size_t nbits);
 void blst_p2_cneg(blst_p2 *p, bool cbit);
 void blst_p2_affine_compress(uint8_t out[96], const blst_p2_affine *in);               /* blst.h:314 */
+void blst_p1_affine_compress(uint8_t out[48], const blst_p1_affine *in);               /* blst.h:310 */
+void blst_p1_affine_serialize(uint8_t out[96], const blst_p1_affine *in);
+void blst_p2_affine_serialize(uint8_t out[192], const blst_p2_affine *in);
+int blst_p1_uncompress(blst_p1_affine *out, const uint8_t in[48]);                     /* blst.h:311 */
+int blst_p1_deserialize(blst_p1_affine *out, const uint8_t in[96]);
+int blst_p2_uncompress(blst_p2_affine *out, const uint8_t in[96]);                     /* blst.h:315 */
+int blst_p2_deserialize(blst_p2_affine *out, const uint8_t in[192]);
+bool blst_p1_affine_is_inf(const blst_p1_affine *a);                                   /* blst.h:192 */
+bool blst_p1_affine_in_g1(const blst_p1_affine *p);                                    /* blst.h:191 */
+bool blst_p2_affine_in_g2(const blst_p2_affine *p);                                    /* blst.h:218 */
+bool blst_p1_affine_on_curve(const blst_p1_affine *p);
+bool blst_p2_affine_on_curve(const blst_p2_affine *p);
 
 size_t blst_p1s_mult_pippenger_scratch_sizeof(size_t npoints);                         /* blst.h:242 */
 void blst_p1s_mult_pippenger(blst_p1 *ret, const blst_p1_affine *const points[], size_t npoints,
@@ -67,6 +79,10 @@ int blst_pairing_chk_n_mul_n_aggr_pk_in_g1(blst_pairing *ctx, const blst_p1_affi
                                            const uint8_t *scalar, size_t nbits,
                                            const uint8_t *msg, size_t msg_len,
                                            const uint8_t *aug, size_t aug_len);        /* blst.h:425 */
+int blst_pairing_chk_n_aggr_pk_in_g1(blst_pairing *ctx, const blst_p1_affine *PK, bool pk_grpchk,
+                                     const blst_p2_affine *sig, bool sig_grpchk,
+                                     const uint8_t *msg, size_t msg_len,
+                                     const uint8_t *aug, size_t aug_len);              /* blst.h:417 */
 int blst_pairing_merge(blst_pairing *ctx, const blst_pairing *ctx1);                   /* blst.h:436 */
 bool blst_pairing_finalverify(const blst_pairing *ctx, const blst_fp12 *gtsig);        /* blst.h:437 */
 blst_fp12 *blst_pairing_as_fp12(blst_pairing *ctx);                                    /* blst_aux.h:87 */

@@ -213,3 +213,71 @@ def finalize(partials):
     gt = _out(576)
     ok = ref.ref_finalize(_buf(partials), C.c_size_t(count), gt)
     return bool(ok), bytes(gt)
+
+
+# ---- aggregateVerify / fastAggregateVerify (bls_sig_min_pubkey.nim:127-273) ----
+ref.ref_aggregate_verify.restype = C.c_int
+ref.ref_fast_aggregate_verify.restype = C.c_int
+ref.ref_pubkey_from_bytes.restype = C.c_int
+ref.ref_signature_from_bytes.restype = C.c_int
+DST_ETH2 = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_"
+
+
+def _offsets(msgs):
+    offs, o = [0], 0
+    for m in msgs:
+        o += len(m)
+        offs.append(o)
+    return (C.c_uint32 * len(offs))(*offs)
+
+
+def aggregate_verify(pubkeys96, msgs, sig192, dst=DST_ETH2):
+    """(bool, GT bytes) of aggregateVerify over n (public key, message) pairs and one signature."""
+    n = len(pubkeys96) // 96
+    assert n == len(msgs)
+    gt = _out(576)
+    blob = b"".join(msgs)
+    ok = ref.ref_aggregate_verify(_buf(pubkeys96) if n else None, C.c_size_t(n), _buf(blob) if blob else None,
+                                  _offsets(msgs), _buf(dst), C.c_size_t(len(dst)), _buf(sig192), gt)
+    return bool(ok), bytes(gt)
+
+
+def fast_aggregate_verify(pubkeys96, msg, sig192, dst=DST_ETH2):
+    n = len(pubkeys96) // 96
+    gt = _out(576)
+    ok = ref.ref_fast_aggregate_verify(_buf(pubkeys96) if n else None, C.c_size_t(n), _buf(msg) if msg else None,
+                                       C.c_size_t(len(msg)), _buf(dst), C.c_size_t(len(dst)), _buf(sig192), gt)
+    return bool(ok), bytes(gt)
+
+
+# ---- SURVEY.md §8f N2: fromBytes with checks (bls_sig_io.nim:42-122) ----
+def pubkey_from_bytes(raw, group_check=True):
+    """(BLST_ERROR, 96-byte affine) of PublicKey.fromBytes on 48 (compressed) or 96 (serialized) bytes."""
+    out = _out(96)
+    err = ref.ref_pubkey_from_bytes(_buf(raw), C.c_size_t(len(raw)), C.c_int(1 if group_check else 0), out)
+    return int(err), bytes(out)
+
+
+def signature_from_bytes(raw, group_check=True):
+    out = _out(192)
+    err = ref.ref_signature_from_bytes(_buf(raw), C.c_size_t(len(raw)), C.c_int(1 if group_check else 0), out)
+    return int(err), bytes(out)
+
+
+def g1_serialize(aff96):
+    c, s = _out(48), _out(96)
+    ref.ref_g1_compress(_buf(aff96), c, s)
+    return bytes(s)
+
+
+def g2_serialize(aff192):
+    c, s = _out(96), _out(192)
+    ref.ref_g2_compress(_buf(aff192), c, s)
+    return bytes(s)
+
+
+def sign(seed, msg, dst=DST_ETH2):
+    """(pk 96 B, sig 192 B) of the key derived from `seed` over an arbitrary-length message under `dst`."""
+    pk, sig = _out(96), _out(192)
+    ref.ref_sign(C.c_uint64(seed), _buf(msg) if msg else None, C.c_size_t(len(msg)), _buf(dst), C.c_size_t(len(dst)), pk, sig)
+    return bytes(pk), bytes(sig)

@@ -465,3 +465,97 @@ int ref_finalize(const uint8_t *partials, size_t count, uint8_t gt_out[576]) {
     blst_bendian_from_fp12(gt_out, &acc);
     return blst_fp12_is_one(&acc) ? 1 : 0;
 }
+
+/* ---------------- aggregateVerify / fastAggregateVerify / verify ----------------
+ * bls_sig_min_pubkey.nim:127-273 over ContextCoreAggregateVerify (blst_min_pubkey_sig_core.nim:310-398): update() per
+ * (publicKey, message) with no signature, finish() adds the signature through the same call with PK = nil, then
+ * commit + finalverify.  n pairs, arbitrary message lengths (msg i = msgs[offs[i] .. offs[i+1])), caller's DST.
+ * GT bytes are recomputed like in ref_batch_verify (informative on failing inputs). */
+int ref_aggregate_verify(const uint8_t *pks, size_t n, const uint8_t *msgs, const uint32_t *offs,
+                         const uint8_t *dst, size_t dst_len, const uint8_t sig[192], uint8_t gt_out[576]) {
+    static const uint8_t zero[192];
+    memset(gt_out, 0, 576);
+    if (n == 0) return 0;                                   /* bls_sig_min_pubkey.nim:140, :167, :189, :214 */
+    blst_pairing *ctx = malloc(blst_pairing_sizeof());
+    blst_pairing_init(ctx, 1, dst, dst_len);
+    int ok = 1;
+    for (size_t i = 0; i < n && ok; i++)
+        ok = blst_pairing_chk_n_aggr_pk_in_g1(ctx, (const blst_p1_affine *)(pks + 96 * i), 0, NULL, 0,
+                                              msgs + offs[i], offs[i + 1] - offs[i], NULL, 0) == 0;
+    if (ok) ok = blst_pairing_chk_n_aggr_pk_in_g1(ctx, NULL, 0, (const blst_p2_affine *)sig, 0, NULL, 0, NULL, 0) == 0;
+    if (ok) {
+        blst_pairing_commit(ctx);
+        int verdict = blst_pairing_finalverify(ctx, NULL) ? 1 : 0;
+        blst_fp12 gt, acc;
+        if (memcmp(sig, zero, 192) != 0) blst_miller_loop(&gt, (const blst_p2_affine *)sig, blst_p1_affine_generator());
+        else gt = *blst_fp12_one();
+        blst_fp12_conjugate(&gt);
+        acc = *blst_pairing_as_fp12(ctx);
+        blst_fp12_mul(&gt, &gt, &acc);
+        blst_final_exp(&gt, &gt);
+        blst_bendian_from_fp12(gt_out, &gt);
+        if (blst_fp12_is_one(&gt) != (verdict != 0)) {
+            fprintf(stderr, "ref_aggregate_verify: GT recomputation disagrees with blst_pairing_finalverify\n");
+            abort();
+        }
+        ok = verdict;
+    }
+    free(ctx);
+    return ok;
+}
+
+/* fastAggregateVerify(publicKeys, message, signature), bls_sig_min_pubkey.nim:238-258: aggregateAll + coreVerify */
+int ref_fast_aggregate_verify(const uint8_t *pks, size_t n, const uint8_t *msg, size_t msg_len,
+                              const uint8_t *dst, size_t dst_len, const uint8_t sig[192], uint8_t gt_out[576]) {
+    uint8_t agg[96];
+    uint32_t offs[2] = {0, (uint32_t)msg_len};
+    memset(gt_out, 0, 576);
+    if (!ref_aggregate_g1(pks, n, agg)) return 0;
+    return ref_aggregate_verify(agg, 1, msg, offs, dst, dst_len, sig, gt_out);
+}
+
+/* ---------------- deserialisation + checks ----------------
+ * PublicKey.fromBytes / Signature.fromBytes, bls_sig_io.nim:42-122: uncompress (48/96 B) or deserialize (96/192 B),
+ * public keys reject infinity, then the subgroup check.  Returns the BLST_ERROR (0 = success; 1 bad encoding,
+ * 2 not on curve, 3 not in group, 6 public key is infinity) and writes the affine point on success. */
+int ref_pubkey_from_bytes(const uint8_t *in, size_t len, int group_check, uint8_t out[96]) {
+    blst_p1_affine a;
+    int err = len == 48 ? blst_p1_uncompress(&a, in) : blst_p1_deserialize(&a, in);
+    memset(out, 0, 96);
+    if (err) return err;
+    if (blst_p1_affine_is_inf(&a)) return 6;                /* BLST_PK_IS_INFINITY */
+    if (group_check && !blst_p1_affine_in_g1(&a)) return 3; /* BLST_POINT_NOT_IN_GROUP */
+    memcpy(out, &a, 96);
+    return 0;
+}
+
+int ref_signature_from_bytes(const uint8_t *in, size_t len, int group_check, uint8_t out[192]) {
+    blst_p2_affine a;
+    int err = len == 96 ? blst_p2_uncompress(&a, in) : blst_p2_deserialize(&a, in);
+    memset(out, 0, 192);
+    if (err) return err;
+    if (group_check && !blst_p2_affine_in_g2(&a)) return 3;
+    memcpy(out, &a, 192);
+    return 0;
+}
+
+void ref_g1_compress(const uint8_t in[96], uint8_t out48[48], uint8_t out96[96]) {
+    blst_p1_affine_compress(out48, (const blst_p1_affine *)in);
+    blst_p1_affine_serialize(out96, (const blst_p1_affine *)in);
+}
+void ref_g2_compress(const uint8_t in[192], uint8_t out96[96], uint8_t out192[192]) {
+    blst_p2_affine_compress(out96, (const blst_p2_affine *)in);
+    blst_p2_affine_serialize(out192, (const blst_p2_affine *)in);
+}
+
+/* sign an arbitrary-length message under the caller's DST with the key of `seed` (coreSign, blst_min_pubkey_sig_core.nim:250-262) */
+void ref_sign(uint64_t seed, const uint8_t *msg, size_t len, const uint8_t *dst, size_t dst_len, uint8_t pk_out[96],
+              uint8_t sig_out[192]) {
+    blst_scalar sk; blst_p1 pk; blst_p2 h;
+    keygen_seed(&sk, seed);
+    blst_sk_to_pk_in_g1(&pk, &sk);
+    blst_p1_to_affine((blst_p1_affine *)pk_out, &pk);
+    blst_hash_to_g2(&h, msg, len, dst, dst_len, NULL, 0);
+    blst_sign_pk_in_g1(&h, &h, &sk);
+    blst_p2_to_affine((blst_p2_affine *)sig_out, &h);
+}

@@ -8,6 +8,7 @@
 #include <string.h>
 #include "../../nim_blscurve_b200/csrc/h2c.cuh"
 #include "../../nim_blscurve_b200/csrc/pairing.cuh"
+#include "../../nim_blscurve_b200/csrc/io.cuh"
 #include "../../nim_blscurve_b200/csrc/fpprog.hpp"
 using namespace bls;
 
@@ -146,5 +147,8 @@ int hs_prog_combine(const fp12 *seg, int nseg, fp12 *out, int *stats) {
     stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
     return 1;
 }
+int hs_pubkey_from_bytes(const uint8_t *in, int len, int group_check, g1_aff *out) { return pubkey_from_bytes(*out, in, len, group_check != 0); }
+int hs_signature_from_bytes(const uint8_t *in, int len, int group_check, g2_aff *out) { return signature_from_bytes(*out, in, len, group_check != 0); }
+void hs_g1_compress(const g1_aff *p, uint8_t *out) { g1_compress(out, *p); }
 void hs_miller_combine(const fp12 *seg, int nseg, fp12 *out) { miller_combine(*out, seg, nseg); }
 }

@@ -204,3 +204,45 @@ def test_g1_mul_windowed(hs):
     o1 = out(96)
     hs.hs_g1_mul_u64_w4(buf(bytes(96)), C.c_uint64(12345), o1)
     assert bytes(o1) == bytes(96)
+
+
+def test_from_bytes_with_checks(hs, br):
+    """io.cuh on the host against BLST: every exit of uncompress / deserialize, infinity rule, subgroup tests."""
+    rng = random.Random(11)
+    sets = br.make_sets(500, 3)
+    g1_cases = [br.g1_compress(sets[320 * i:320 * i + 96]) for i in range(3)]
+    good = g1_cases[0]
+    g1_cases += [bytes([good[0] ^ 0x20]) + good[1:], bytes([good[0] & 0x7f]) + good[1:], bytes([0xc0]) + bytes(47),
+                 bytes([0xc0]) + bytes(46) + b"\x01", bytes([0x80 | 0x1a]) + P.to_bytes(48, "big")[1:],
+                 bytes([0x80]) + bytes(47)]
+    g1_cases += [bytes([0x80]) + x.to_bytes(47, "big") for x in range(1, 12)]
+    g1_cases += [br.g1_serialize(sets[:96]), bytes([0x40]) + bytes(95), bytes(96), good + bytes(48)]
+    seen = set()
+    for c in g1_cases:
+        for gc in (1, 0):
+            o = out(96)
+            err = hs.hs_pubkey_from_bytes(buf(c), len(c), gc, o)
+            werr, wpt = br.pubkey_from_bytes(c, group_check=bool(gc))
+            assert (err, bytes(o)) == (werr, wpt), (c.hex(), gc)
+            seen.add(err)
+    assert seen >= {0, 1, 2, 3, 6}
+    o = out(48)
+    hs.hs_g1_compress(buf(sets[:96]), o)
+    assert bytes(o) == good
+    g2_cases = [br.g2_compress(sets[320 * i + 128:320 * i + 320]) for i in range(3)]
+    good = g2_cases[0]
+    g2_cases += [bytes([good[0] ^ 0x20]) + good[1:], bytes([0xc0]) + bytes(95), good[:48] + P.to_bytes(48, "big"),
+                 bytes([0x80]) + bytes(95), br.g2_serialize(sets[128:320]), bytes(192), bytes([0x40]) + bytes(191)]
+    for _ in range(8):
+        b = bytearray(rng.randrange(P).to_bytes(48, "big") + rng.randrange(P).to_bytes(48, "big"))
+        b[0] = (b[0] & 0x1f) | 0x80
+        g2_cases.append(bytes(b))
+    seen = set()
+    for c in g2_cases:
+        for gc in (1, 0):
+            o = out(192)
+            err = hs.hs_signature_from_bytes(buf(c), len(c), gc, o)
+            werr, wpt = br.signature_from_bytes(c, group_check=bool(gc))
+            assert (err, bytes(o)) == (werr, wpt), (c.hex(), gc)
+            seen.add(err)
+    assert seen >= {0, 1, 2, 3}
