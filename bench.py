@@ -96,6 +96,67 @@ def run_reference(args):
     return 0
 
 
+def bench_msm(L, h, cache, stream, flush, peak_wide, hbm_peak, args):
+    """BASELINE metric, second half: G1 MSM over 2^20 points, ms (benchmarks/bls12381_msm_g1.nim shape: 96-bit-multiple
+    points, 255-bit scalars).  Inputs generated on the device; timed with CUDA events on the launching stream, L2 flushed
+    between repetitions.  Roofline: reference-algorithm work W_pt = 176 Fp-mul per point at 2^20 x 300
+    IMAD against the measured IMAD.WIDE peak; HBM bytes (points + scalars read once) as the secondary figure.
+    CPU beside it: BLST blst_p1s_mult_pippenger, ONE thread (the reference benchmark is single-threaded), same inputs —
+    which also makes this a full-size parity check of the affine result."""
+    import torch
+    k = args.msm_log2
+    n = 1 << k
+    dev = flush.device
+    dp = torch.empty(n * 96, dtype=torch.uint8, device=dev)
+    ds = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    assert L.blsgpu_msm_make_inputs(h, 0xFACADE, n, C.c_void_p(dp.data_ptr()), C.c_void_p(ds.data_ptr())) == 0
+    out = (C.c_uint8 * 96)()
+    for _ in range(3):
+        assert L.blsgpu_msm_g1_dev(h, C.c_void_p(dp.data_ptr()), C.c_void_p(ds.data_ptr()), n, 255, out) == 1
+    reps, tot = 5, 0.0
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        L.blsgpu_msm_g1_dev(h, C.c_void_p(dp.data_ptr()), C.c_void_p(ds.data_ptr()), n, 255, out)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / reps
+    launches = L.blsgpu_last_launches(h)
+    # e2e: host points + scalars -> H2D -> MSM -> affine result back
+    hp, hs = dp.cpu().pin_memory(), ds.cpu().pin_memory()
+    t0 = time.perf_counter()
+    assert L.blsgpu_msm_g1(h, C.c_void_p(hp.data_ptr()), C.c_void_p(hs.data_ptr()), n, 255, out) == 1
+    t0 = time.perf_counter()
+    for _ in range(3):
+        L.blsgpu_msm_g1(h, C.c_void_p(hp.data_ptr()), C.c_void_p(hs.data_ptr()), n, 255, out)
+    ms_e2e = (time.perf_counter() - t0) / 3 * 1e3
+    w_pt = {16: 235, 17: 220, 18: 205, 19: 190, 20: 176, 21: 170, 22: 165}.get(k, 176)
+    res = {"metric": "G1 MSM 2^%d points" % k, "value": ms, "unit": "ms", "higher_is_better": False, "n": n, "nbits": 255,
+           "points_per_s": n / (ms * 1e-3), "gpu_launches": launches,
+           "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes": n * 128, "d2h_bytes": 96},
+           "roofline": {"bound": "int_mul_pipe", "achieved": n * w_pt * IMAD_PER_FPMUL / (ms * 1e-3) / 1e9,
+                        "peak": peak_wide / 1e9, "unit": "G IMAD.WIDE/s",
+                        "frac": n * w_pt * IMAD_PER_FPMUL / (ms * 1e-3) / peak_wide,
+                        "algorithmic_fpmul_per_point": w_pt,
+                        "hbm": {"achieved_gbs": n * 128 / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                "note": "points + scalars read once = 128 B/point: not the bound"}}}
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import blst_ref as br
+            ref_out = (C.c_uint8 * 96)()
+            t0 = time.perf_counter()
+            br.ref.ref_msm_g1(C.c_void_p(hp.data_ptr()), C.c_void_p(hs.data_ptr()), C.c_size_t(n), C.c_size_t(255), ref_out)
+            tc = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": tc * 1e3, "unit": "ms", "cores": 1, "kind": "reference",
+                                   "sample": "the same 2^%d inputs, blst_p1s_mult_pippenger + to_affine, one run" % k}
+            res["matches_reference"] = bytes(ref_out) == bytes(out)
+        except Exception as ex:
+            res["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -104,6 +165,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sets-per-gpu", type=int, default=SETS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-msm", action="store_true", help="skip the G1 MSM 2^20 extra")
+    ap.add_argument("--msm-log2", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -252,7 +315,26 @@ def main():
         for _ in range(reps):
             rcb = L.blsgpu_batch_verify_dev(h, C.c_void_p(d_sets.data_ptr()), blk, srb, 4, None, gt)
         tb = (time.perf_counter() - t0) / reps
-        extra["block_batch"] = {"sets": blk, "ms": tb * 1e3, "sets_per_s": blk / tb, "verified": rcb == 1}
+        extra["block_batch"] = {"sets": blk, "ms": tb * 1e3, "sets_per_s": blk / tb, "verified": rcb == 1,
+                                "what": "BASELINE configs[1]: 129-set batch (128 attestations + 1 sync committee), host call "
+                                        "blsgpu_batch_verify_dev, wall clock; latency-bound"}
+        # the same block with the public-key aggregation done on the GPU first: 128 committees x 128 keys + one of 512
+        # (member keys = public keys of the synthetic sets; one segmented aggregateAll launch, host buffers)
+        nkeys = min(128 * 128 + 512, (S // 129) * 129)
+        member = bytes(h_sets[:nkeys * 320].numpy().reshape(nkeys, 320)[:, :96].tobytes())
+        offs = [min(128 * i, nkeys) for i in range(129)] + [nkeys]
+        c_offs = (C.c_uint32 * len(offs))(*offs)
+        agg_out = (C.c_uint8 * (96 * 129))()
+        for _ in range(2):
+            L.blsgpu_aggregate_g1_segments(h, member, c_offs, 129, agg_out)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            rca = L.blsgpu_aggregate_g1_segments(h, member, c_offs, 129, agg_out)
+        ta = (time.perf_counter() - t0) / reps
+        extra["block_batch"].update({"key_aggregation_ms": ta * 1e3, "keys_aggregated": nkeys, "aggregation_ok": rca == 1,
+                                     "ms_with_key_aggregation": (tb + ta) * 1e3})
+        if not args.no_msm:
+            extra["msm_g1"] = bench_msm(L, h, cache, stream, flush, peak_wide, hbm_peak, args)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import blst_ref as br

@@ -98,4 +98,54 @@ func aggregateAll*(cache: var BatchedBLSVerifierCache, dst: var PublicKey, elems
 func aggregateAll*(cache: var BatchedBLSVerifierCache, dst: var Signature, elems: openArray[Signature]): bool =
   if elems.len == 0: return false
   blsgpu_aggregate_g2(cache.ctx, unsafeAddr elems[0], elems.len.csize_t, addr dst) == 1
+
+# --- SURVEY §8f N3: bls_sig_min_pubkey.nim:108-258 on the device (proof-of-possession overloads stay as they are:
+# they call popVerify per key and then these) ---
+const DST = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_"        # bls_sig_min_pubkey.nim:31
+
+func verify*[T: byte|char](cache: var BatchedBLSVerifierCache, publicKey: PublicKey, message: openArray[T],
+                           signature: Signature): bool =
+  ## coreVerifyNoGroupCheck (blst_min_pubkey_sig_core.nim:264-297) = aggregateVerify over one pair
+  var offs = [0'u32, uint32 message.len]
+  blsgpu_aggregate_verify(cache.ctx, unsafeAddr publicKey, 1, (if message.len > 0: cast[ptr byte](unsafeAddr message[0]) else: nil),
+                          addr offs[0], cast[ptr byte](unsafeAddr DST[0]), DST.len.csize_t, unsafeAddr signature, nil) == 1
+
+func fastAggregateVerify*[T: byte|char](cache: var BatchedBLSVerifierCache, publicKeys: openArray[PublicKey],
+                                        message: openArray[T], signature: Signature): bool =
+  if publicKeys.len == 0: return false                       # :251-253
+  blsgpu_fast_aggregate_verify(cache.ctx, unsafeAddr publicKeys[0], publicKeys.len.csize_t,
+                               (if message.len > 0: cast[ptr byte](unsafeAddr message[0]) else: nil), message.len.csize_t,
+                               cast[ptr byte](unsafeAddr DST[0]), DST.len.csize_t, unsafeAddr signature, nil) == 1
+
+func aggregateVerify*(cache: var BatchedBLSVerifierCache, publicKeys: openArray[PublicKey],
+                      messages: openArray[seq[byte]], signature: Signature): bool =
+  if publicKeys.len != messages.len or publicKeys.len < 1: return false     # :164-169
+  var blob: seq[byte]
+  var offs = newSeq[uint32](messages.len + 1)
+  for i, m in messages:
+    blob.add m
+    offs[i + 1] = uint32 blob.len
+  blsgpu_aggregate_verify(cache.ctx, unsafeAddr publicKeys[0], publicKeys.len.csize_t,
+                          (if blob.len > 0: addr blob[0] else: nil), addr offs[0],
+                          cast[ptr byte](unsafeAddr DST[0]), DST.len.csize_t, unsafeAddr signature, nil) == 1
+
+# --- SURVEY §8f N2: bls_sig_io.nim:42-122, batched ---
+func fromBytes*(cache: var BatchedBLSVerifierCache, dst: var openArray[PublicKey], raw: openArray[array[48, byte]],
+                ok: var openArray[bool]): bool =
+  ## every element as PublicKey.fromBytes: uncompress, reject infinity, subgroup check
+  doAssert dst.len == raw.len and ok.len == raw.len
+  if raw.len == 0: return true
+  var status = newSeq[byte](raw.len)
+  result = blsgpu_pubkeys_from_bytes(cache.ctx, cast[ptr byte](unsafeAddr raw[0]), raw.len.csize_t, 48, 1,
+                                     addr dst[0], addr status[0]) == 1
+  for i in 0 ..< raw.len: ok[i] = status[i] == 0
+
+func fromBytes*(cache: var BatchedBLSVerifierCache, dst: var openArray[Signature], raw: openArray[array[96, byte]],
+                ok: var openArray[bool]): bool =
+  doAssert dst.len == raw.len and ok.len == raw.len
+  if raw.len == 0: return true
+  var status = newSeq[byte](raw.len)
+  result = blsgpu_signatures_from_bytes(cache.ctx, cast[ptr byte](unsafeAddr raw[0]), raw.len.csize_t, 96, 1,
+                                        addr dst[0], addr status[0]) == 1
+  for i in 0 ..< raw.len: ok[i] = status[i] == 0
 {.pop.}

@@ -37,6 +37,18 @@ proc blsgpu_aggregate_g1*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: poin
 proc blsgpu_aggregate_g2*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: pointer): cint
 proc blsgpu_msm_g1*(ctx: BlsGpuCtx, points, scalars: pointer, n, nbits: csize_t, dst: pointer): cint
 proc blsgpu_msm_g2*(ctx: BlsGpuCtx, points, scalars: pointer, n, nbits: csize_t, dst: pointer): cint
+proc blsgpu_aggregate_g1_segments*(ctx: BlsGpuCtx, points: pointer, offsets: ptr uint32, nseg: csize_t,
+                                   dst: pointer): cint
+proc blsgpu_aggregate_verify*(ctx: BlsGpuCtx, pubkeys: pointer, n: csize_t, msgs: ptr byte, msgOffsets: ptr uint32,
+                              dst: ptr byte, dstLen: csize_t, sig: pointer, gtOut: ptr array[576, byte]): cint
+proc blsgpu_fast_aggregate_verify*(ctx: BlsGpuCtx, pubkeys: pointer, n: csize_t, msg: ptr byte, msgLen: csize_t,
+                                   dst: ptr byte, dstLen: csize_t, sig: pointer, gtOut: ptr array[576, byte]): cint
+proc blsgpu_pubkeys_from_bytes*(ctx: BlsGpuCtx, raw: ptr byte, n, inLen: csize_t, groupCheck: cint,
+                                dst: pointer, status: ptr byte): cint
+proc blsgpu_signatures_from_bytes*(ctx: BlsGpuCtx, raw: ptr byte, n, inLen: csize_t, groupCheck: cint,
+                                   dst: pointer, status: ptr byte): cint
+proc blsgpu_pubkeys_to_bytes*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: ptr byte): cint
+proc blsgpu_signatures_to_bytes*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: ptr byte): cint
 proc blsgpu_combine*(ctx: BlsGpuCtx, srb: ptr array[32, byte], pubkeys, sigs: pointer, n: csize_t,
                      pkOut, sigOut: pointer): cint
 {.pop.}
