@@ -127,6 +127,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     if (e != cudaSuccess) return bad("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
     ctx->stream = ctx->own_stream;
+    { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->msm.sms = sms; }
     size_t n = max_sets;
 #define ALLOC(ptr, bytes) if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return bad("cudaMalloc " #ptr, e)
     ALLOC(ctx->d_sets, n * sizeof(sigset));

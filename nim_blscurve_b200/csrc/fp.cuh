@@ -296,7 +296,21 @@ BLS_FN void fp_mul(fp &r, const fp &a, const fp &b) {
 #endif
 }
 
-BLS_FN void fp_sqr(fp &r, const fp &a) { fp_mul(r, a, a); }
+}  // namespace bls
+#include "fp_gen.cuh"
+namespace bls {
+
+// Montgomery square.  Device: dedicated squaring (fp_gen.cuh: 78 product terms instead of 144, 234 IMADs instead of
+// 300) unless BLS_NO_FP_SQR; the host build multiplies.
+BLS_FN void fp_sqr(fp &r, const fp &a) {
+#if defined(__CUDA_ARCH__) && !defined(BLS_NO_FP_SQR)
+    uint32_t t[12];
+    fp_sqr_ptx(t, a.l);
+    reduce_once12(r.l, t);
+#else
+    fp_mul(r, a, a);
+#endif
+}
 
 // out of Montgomery form: r = a/R mod p  (canonical integer limbs)
 BLS_FN void fp_from_mont(fp &r, const fp &a) {

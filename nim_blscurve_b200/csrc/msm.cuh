@@ -4,11 +4,12 @@
 // so the GPU decomposition is free to differ:
 //   1. k_msm_count    signed window digits (Booth-style carry, digits in (-2^(c-1), 2^(c-1)]), histogram
 //                     of (window, |digit|) with global atomics
-//   2. k_msm_scan     exclusive prefix sums of the histogram and of the per-bucket task counts (one block)
+//   2. k_msm_scan_*   exclusive prefix sums of the histogram and of the non-empty flags (three launches)
 //   3. k_msm_scatter  counting-sort scatter of (point index, sign) into bucket order
-//   4. k_msm_task     one thread per TASK = at most `ch` consecutive entries of one bucket: gathers its points,
-//                     mixed Jacobian additions -> one partial per task (a bucket of any size is split evenly,
-//                     so a skewed digit distribution cannot serialise the kernel)
+//   4. k_msm_chunks   one thread per CHUNK = K consecutive entries of the sorted list, whatever buckets they fall in:
+//                     gathers its points, mixed Jacobian additions, one partial per (chunk, bucket) run - every lane
+//                     does exactly K additions, so neither a skewed digit distribution nor the spread of bucket
+//                     sizes idles lanes
 //   5. k_msm_combine  one thread per bucket sums its partials; buckets with more than MSM_BIG partials are
 //                     deferred to k_msm_combine_big (one warp per bucket, shuffle tree)
 //   6. k_msm_segment  running-sum integration of L-bucket segments, weighted by the segment base
@@ -27,6 +28,7 @@ namespace bls {
 struct msm_state {
     uint8_t *buf = nullptr;
     size_t bytes = 0;
+    int sms = 148;                 // SM count of the device (B200: 148); set at context creation
 };
 
 static inline void msm_free(msm_state &m) {
@@ -72,40 +74,71 @@ __global__ void __launch_bounds__(256) k_msm_count(const uint8_t *scalars, size_
     }
 }
 
-// Exclusive scans over m buckets (single block of 1024 threads):
-//   offsets[0..m] of the entry counts (cursor = a working copy for the scatter), toff[0..m] of ceil(count / ch).
-__global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *counts, size_t m, uint32_t ch, uint32_t *offsets,
-                                                   uint32_t *cursor, uint32_t *toff) {
-    __shared__ uint32_t ws[2][32];
+// Exclusive scans over the m buckets, three launches (block sums -> scan of the block sums -> apply):
+//   offsets[0..m] of the entry counts (cursor = a working copy for the scatter), rank[0..m] of [count > 0]
+//   (rank[b] = number of non-empty buckets before b; it places the partial sums, see k_msm_chunks).
+__device__ __forceinline__ void msm_block_scan2(uint32_t v0, uint32_t v1, uint32_t &x0, uint32_t &x1, uint32_t &t0, uint32_t &t1,
+                                                uint32_t (*ws)[32]) {
+    // inclusive scans x0/x1 of v0/v1 over the 1024 threads of the block, block totals in t0/t1
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    x0 = v0; x1 = v1;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+        if (lane >= o) { x0 += y0; x1 += y1; }
+    }
+    if (lane == 31) { ws[0][wid] = x0; ws[1][wid] = x1; }
+    __syncthreads();
+    if (wid < 2) {
+        uint32_t s = ws[wid][lane], t = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        ws[wid][lane] = t - s;            // exclusive warp offsets
+        if (lane == 31) ws[2 + wid][0] = t;
+    }
+    __syncthreads();
+    x0 += ws[0][wid];
+    x1 += ws[1][wid];
+    t0 = ws[2][0];
+    t1 = ws[3][0];
+}
+
+__global__ void __launch_bounds__(1024) k_msm_scan_blocks(const uint32_t *counts, size_t m, uint32_t *bsums) {
+    __shared__ uint32_t ws[4][32];
+    size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    uint32_t v0 = i < m ? counts[i] : 0, v1 = v0 ? 1u : 0u, x0, x1, t0, t1;
+    msm_block_scan2(v0, v1, x0, x1, t0, t1, ws);
+    if (threadIdx.x == 0) { bsums[2 * blockIdx.x] = t0; bsums[2 * blockIdx.x + 1] = t1; }
+}
+
+// in-place exclusive scan of the nblk (entries, non-empty) pairs; one block
+__global__ void __launch_bounds__(1024) k_msm_scan_top(uint32_t *bsums, size_t nblk) {
+    __shared__ uint32_t ws[4][32];
     __shared__ uint32_t carry_s[2];
     if (threadIdx.x < 2) carry_s[threadIdx.x] = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (size_t base = 0; base < m; base += 1024) {
+    for (size_t base = 0; base < nblk; base += 1024) {
         size_t i = base + threadIdx.x;
-        uint32_t v0 = i < m ? counts[i] : 0, v1 = (v0 + ch - 1) / ch, x0 = v0, x1 = v1;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
-            if (lane >= o) { x0 += y0; x1 += y1; }
-        }
-        if (lane == 31) { ws[0][wid] = x0; ws[1][wid] = x1; }
+        uint32_t v0 = i < nblk ? bsums[2 * i] : 0, v1 = i < nblk ? bsums[2 * i + 1] : 0, x0, x1, t0, t1;
+        msm_block_scan2(v0, v1, x0, x1, t0, t1, ws);
+        uint32_t c0 = carry_s[0], c1 = carry_s[1];
+        if (i < nblk) { bsums[2 * i] = c0 + x0 - v0; bsums[2 * i + 1] = c1 + x1 - v1; }
         __syncthreads();
-        if (wid < 2) {
-            uint32_t s = ws[wid][lane], t = s;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t += y;
-            }
-            ws[wid][lane] = t - s;        // exclusive warp offsets
-        }
-        __syncthreads();
-        uint32_t e0 = carry_s[0] + ws[0][wid] + x0 - v0, e1 = carry_s[1] + ws[1][wid] + x1 - v1;
-        if (i < m) { offsets[i] = e0; cursor[i] = e0; toff[i] = e1; }
-        __syncthreads();
-        if (threadIdx.x == 1023) { carry_s[0] = e0 + v0; carry_s[1] = e1 + v1; }
+        if (threadIdx.x == 0) { carry_s[0] = c0 + t0; carry_s[1] = c1 + t1; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { offsets[m] = carry_s[0]; toff[m] = carry_s[1]; }
+}
+
+__global__ void __launch_bounds__(1024) k_msm_scan_apply(const uint32_t *counts, size_t m, const uint32_t *bsums,
+                                                         uint32_t *offsets, uint32_t *cursor, uint32_t *rank) {
+    __shared__ uint32_t ws[4][32];
+    size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    uint32_t v0 = i < m ? counts[i] : 0, v1 = v0 ? 1u : 0u, x0, x1, t0, t1;
+    msm_block_scan2(v0, v1, x0, x1, t0, t1, ws);
+    uint32_t e0 = bsums[2 * blockIdx.x] + x0 - v0, e1 = bsums[2 * blockIdx.x + 1] + x1 - v1;
+    if (i < m) { offsets[i] = e0; cursor[i] = e0; rank[i] = e1; }
+    if (i == m - 1) { offsets[m] = e0 + v0; rank[m] = e1 + v1; }
 }
 
 __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *scalars, size_t sstride, size_t n, int sb, int nbits, int c,
@@ -124,46 +157,67 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *scalars, siz
     }
 }
 
-// task t -> (bucket b, chunk): toff[b] <= t < toff[b+1]; sums entries [offsets[b] + chunk*ch, ... + ch) of bucket b
+// Chunk t sums entries [t*K, (t+1)*K) of the bucket-sorted entry list: every lane of a warp performs exactly K mixed
+// additions whatever the digit distribution (no idle lanes, no serialisation on a heavy bucket).  A run of one bucket
+// inside a chunk yields one partial, stored at slot t + rank[b]: slots increase strictly along the (chunk, bucket) run
+// sequence, and the partials of bucket b are the contiguous slots t0 + rank[b] .. t1 + rank[b] for the chunks t0..t1
+// its entries touch.
 template <class F>
-__global__ void BLS_LB k_msm_task(const uint8_t *points, size_t pstride, const uint32_t *offsets, const uint32_t *toff,
-                                  const uint32_t *entries, size_t nb, uint32_t ch, jac_t<F> *partials) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= toff[nb]) return;
-    size_t lo = 0, hi = nb;                        // largest b with toff[b] <= t
+__global__ void BLS_LB k_msm_chunks(const uint8_t *points, size_t pstride, const uint32_t *offsets, const uint32_t *rank,
+                                    const uint32_t *entries, size_t nb, uint32_t K, jac_t<F> *partials) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t E = offsets[nb];
+    if (t * K >= E) return;
+    const uint32_t e0 = (uint32_t)(t * K), e1 = E - e0 > K ? e0 + K : E;
+    size_t lo = 0, hi = nb;                        // largest b with offsets[b] <= e0: the (non-empty) bucket of entry e0
     while (hi - lo > 1) {
         size_t mid = (lo + hi) >> 1;
-        if (toff[mid] <= t) lo = mid; else hi = mid;
+        if (offsets[mid] <= e0) lo = mid; else hi = mid;
     }
-    const size_t b = lo;
-    uint32_t e0 = offsets[b] + (uint32_t)(t - toff[b]) * ch, e1 = offsets[b + 1];
-    if (e1 > e0 + ch) e1 = e0 + ch;
+    size_t b = lo;
+    uint32_t bend = offsets[b + 1];
     jac_t<F> acc;
     pt_set_inf(acc);
     for (uint32_t e = e0; e < e1; e++) {
+        if (e == bend) {                           // bucket boundary: flush the run, move to the next non-empty bucket
+            partials[t + rank[b]] = acc;
+            pt_set_inf(acc);
+            do { b++; bend = offsets[b + 1]; } while (bend <= e);
+        }
         uint32_t ent = entries[e];
         aff_t<F> p = *(const aff_t<F> *)(points + (size_t)(ent >> 1) * pstride);
         if (ent & 1) f_neg(p.y, p.y);
         pt_add_affine(acc, acc, p);
     }
-    partials[t] = acc;
+    partials[t + rank[b]] = acc;
+}
+
+// partial slots of bucket b (count > 0): [base, base + np)
+__device__ __forceinline__ void msm_bucket_slots(const uint32_t *offsets, const uint32_t *rank, size_t b, uint32_t K,
+                                                 uint32_t &base, uint32_t &np) {
+    const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
+    if (o1 == o0) { base = 0; np = 0; return; }
+    const uint32_t t0 = o0 / K, t1 = (o1 - 1) / K;
+    base = t0 + rank[b];
+    np = t1 - t0 + 1;
 }
 
 template <class F>
-__global__ void BLS_LB k_msm_combine(const jac_t<F> *partials, const uint32_t *toff, size_t nb, jac_t<F> *buckets,
-                                     uint32_t *biglist, uint32_t *bigcount) {
+__global__ void BLS_LB k_msm_combine(const jac_t<F> *partials, const uint32_t *offsets, const uint32_t *rank, size_t nb,
+                                     uint32_t K, jac_t<F> *buckets, uint32_t *biglist, uint32_t *bigcount) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    uint32_t t0 = toff[b], t1 = toff[b + 1];
-    if (t1 - t0 > MSM_BIG) {
+    uint32_t base, np;
+    msm_bucket_slots(offsets, rank, b, K, base, np);
+    if (np > MSM_BIG) {
         biglist[atomicAdd(bigcount, 1u)] = (uint32_t)b;
         return;
     }
     jac_t<F> acc;
     pt_set_inf(acc);
-    if (t1 > t0) acc = partials[t0];
-    for (uint32_t t = t0 + 1; t < t1; t++) {
-        jac_t<F> x = partials[t];
+    if (np) acc = partials[base];
+    for (uint32_t t = 1; t < np; t++) {
+        jac_t<F> x = partials[base + t];
         pt_add(acc, acc, x);
     }
     buckets[b] = acc;
@@ -171,17 +225,19 @@ __global__ void BLS_LB k_msm_combine(const jac_t<F> *partials, const uint32_t *t
 
 // one warp per over-full bucket: lanes stride over its partials, then a shuffle tree
 template <class F>
-__global__ void BLS_LB k_msm_combine_big(const jac_t<F> *partials, const uint32_t *toff, const uint32_t *biglist,
-                                         const uint32_t *bigcount, jac_t<F> *buckets) {
+__global__ void BLS_LB k_msm_combine_big(const jac_t<F> *partials, const uint32_t *offsets, const uint32_t *rank, uint32_t K,
+                                         const uint32_t *biglist, const uint32_t *bigcount, jac_t<F> *buckets) {
     const int lane = threadIdx.x & 31;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t nbig = *bigcount;
     for (size_t i = warp; i < nbig; i += nwarps) {
-        const uint32_t b = biglist[i], t0 = toff[b], t1 = toff[b + 1];
+        const uint32_t b = biglist[i];
+        uint32_t base, np;
+        msm_bucket_slots(offsets, rank, b, K, base, np);
         jac_t<F> acc;
         pt_set_inf(acc);
-        for (uint32_t t = t0 + lane; t < t1; t += 32) {
-            jac_t<F> x = partials[t];
+        for (uint32_t t = lane; t < np; t += 32) {
+            jac_t<F> x = partials[base + t];
             pt_add(acc, acc, x);
         }
         for (int o = 16; o >= 1; o >>= 1) {
@@ -303,23 +359,34 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
     msm_shape(n, nbits, c, nwin);
     const size_t B = (size_t)1 << (c - 1);
     const size_t nb = (size_t)nwin * B;
-    const uint32_t ch = sizeof(F) == sizeof(fp) ? 32 : 16;
+    // entries per chunk: the chunk grid fills whole waves of the resident-thread capacity (SMs x 4 blocks x 128) with
+    // about 32 additions per thread; short MSMs get one wave of shorter chunks
+    const size_t emax = n * (size_t)nwin;
+    const size_t wave = (size_t)st.sms * BLS_LB_BLOCKS * 128;
+    size_t waves = emax / (wave * 32);
+    if (waves < 1) waves = 1;
+    size_t Kz = (emax + waves * wave - 1) / (waves * wave);
+    if (Kz < 8) Kz = 8;
+    const uint32_t K = (uint32_t)Kz;
     size_t L = B / 512;                            // segment length: short serial chains, <= 512 segments per window
     if (L < 4) L = 4;
     if (L > 32) L = 32;
     if (L > B) L = B;
     const size_t nseg = B / L;
-    const size_t tmax = n * (size_t)nwin / ch + nb + 1;
+    const size_t nchunks = (emax + K - 1) / K;
+    const size_t pmax = nchunks + nb + 1;          // partial slots: chunk index + rank of the bucket
+    const size_t nsb = (nb + 1023) / 1024;         // scan blocks
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o_counts = 0;
     size_t o_offsets = o_counts + al(nb * 4);
     size_t o_cursor = o_offsets + al((nb + 1) * 4);
-    size_t o_toff = o_cursor + al(nb * 4);
-    size_t o_big = o_toff + al((nb + 1) * 4);
+    size_t o_rank = o_cursor + al(nb * 4);
+    size_t o_bsums = o_rank + al((nb + 1) * 4);
+    size_t o_big = o_bsums + al(nsb * 8);
     size_t o_bigcount = o_big + al(nb * 4);
     size_t o_entries = o_bigcount + 256;
-    size_t o_partials = o_entries + al(n * (size_t)nwin * 4);
-    size_t o_buckets = o_partials + al(tmax * sizeof(J));
+    size_t o_partials = o_entries + al(emax * 4);
+    size_t o_buckets = o_partials + al(pmax * sizeof(J));
     size_t o_segs = o_buckets + al(nb * sizeof(J));
     size_t total = o_segs + al((size_t)nwin * nseg * sizeof(J));
     cudaError_t e;
@@ -332,7 +399,8 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
         st.bytes = total;
     }
     uint32_t *counts = (uint32_t *)(st.buf + o_counts), *offsets = (uint32_t *)(st.buf + o_offsets);
-    uint32_t *cursor = (uint32_t *)(st.buf + o_cursor), *toff = (uint32_t *)(st.buf + o_toff);
+    uint32_t *cursor = (uint32_t *)(st.buf + o_cursor), *rank = (uint32_t *)(st.buf + o_rank);
+    uint32_t *bsums = (uint32_t *)(st.buf + o_bsums);
     uint32_t *biglist = (uint32_t *)(st.buf + o_big), *bigcount = (uint32_t *)(st.buf + o_bigcount);
     uint32_t *entries = (uint32_t *)(st.buf + o_entries);
     J *partials = (J *)(st.buf + o_partials), *buckets = (J *)(st.buf + o_buckets), *segs = (J *)(st.buf + o_segs);
@@ -340,14 +408,16 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
     MCK(cudaMemsetAsync(bigcount, 0, 4, s));
     int nl = 0;
     k_msm_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, sstride, n, sb, nbits, c, nwin, counts);
-    k_msm_scan<<<1, 1024, 0, s>>>(counts, nb, ch, offsets, cursor, toff);
+    k_msm_scan_blocks<<<(unsigned)nsb, 1024, 0, s>>>(counts, nb, bsums);
+    k_msm_scan_top<<<1, 1024, 0, s>>>(bsums, nsb);
+    k_msm_scan_apply<<<(unsigned)nsb, 1024, 0, s>>>(counts, nb, bsums, offsets, cursor, rank);
     k_msm_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, sstride, n, sb, nbits, c, nwin, cursor, entries);
-    k_msm_task<F><<<(unsigned)((tmax + 127) / 128), 128, 0, s>>>(d_points, pstride, offsets, toff, entries, nb, ch, partials);
-    k_msm_combine<F><<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(partials, toff, nb, buckets, biglist, bigcount);
-    k_msm_combine_big<F><<<64, 128, 0, s>>>(partials, toff, biglist, bigcount, buckets);
+    k_msm_chunks<F><<<(unsigned)((nchunks + 127) / 128), 128, 0, s>>>(d_points, pstride, offsets, rank, entries, nb, K, partials);
+    k_msm_combine<F><<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(partials, offsets, rank, nb, K, buckets, biglist, bigcount);
+    k_msm_combine_big<F><<<64, 128, 0, s>>>(partials, offsets, rank, K, biglist, bigcount, buckets);
     size_t nt = (size_t)nwin * nseg;
     k_msm_segment<F><<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(buckets, c, nwin, (uint32_t)L, segs);
-    nl += 7;
+    nl += 9;
     for (size_t m = nseg; m > 1;) {
         size_t half = (m + 1) / 2;
         k_tree_rows<F><<<(unsigned)(((size_t)nwin * half + 127) / 128), 128, 0, s>>>(segs, nwin, nseg, m, half);
