@@ -58,7 +58,8 @@ struct blsgpu_ctx {
     msm_state msm;
     // warp-cooperative tail programs (fpprog.hpp), compiled on first use and kept on the device
     struct dev_prog { uint32_t *d = nullptr; int nslots = 0, nrounds = 0; };
-    std::map<int, dev_prog> combine_progs, final_progs;      // keyed by segment count / partial count
+    std::map<int, dev_prog> combine_progs, final_progs, norm_progs;   // keyed by segment count / partial count
+    fp *d_norm = nullptr;                                    // [0] Fp norm taken out of the final exponentiation, [1] its inverse
     fp *d_consts = nullptr;                                  // Frobenius coefficients (fpprog::CONST_*)
     fp12 *d_gt = nullptr;                                    // final exponentiation result, Montgomery form
     bool serial_tail = false;
@@ -99,7 +100,9 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gtb);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_consts); cudaFree(ctx->d_gt);
     for (auto &kv : ctx->combine_progs) cudaFree(kv.second.d);
-    for (auto &kv : ctx->final_progs) cudaFree(kv.second.d); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
+    for (auto &kv : ctx->final_progs) cudaFree(kv.second.d);
+    for (auto &kv : ctx->norm_progs) cudaFree(kv.second.d);
+    cudaFree(ctx->d_norm); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2 * ST_COUNT + 2; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
@@ -149,6 +152,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     ALLOC(ctx->d_gtb, 576);
     ALLOC(ctx->d_gt, sizeof(fp12));
     ALLOC(ctx->d_consts, fpprog::CONST_COUNT * sizeof(fp));
+    ALLOC(ctx->d_norm, 2 * sizeof(fp));
     ALLOC(ctx->d_flags, 4 * sizeof(int));
 #undef ALLOC
     if ((e = cudaMallocHost((void **)&ctx->h_pinned, 4096)) != cudaSuccess) return bad("cudaMallocHost", e);
@@ -219,9 +223,10 @@ static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size
     return 0;
 }
 
-// Compile (once) and fetch a tail program; kind 0 = combine over `key` segments, 1 = final exponentiation of `key` partials
+// Compile (once) and fetch a tail program; kind 0 = combine over `key` segments, 1 = final exponentiation of `key`
+// partials with the Fp inversion supplied in IN1, 2 = the norm that inversion applies to (fpprog.hpp build_final)
 static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &out) {
-    std::map<int, blsgpu_ctx::dev_prog> &cache = kind == 0 ? ctx->combine_progs : ctx->final_progs;
+    std::map<int, blsgpu_ctx::dev_prog> &cache = kind == 0 ? ctx->combine_progs : (kind == 1 ? ctx->final_progs : ctx->norm_progs);
     auto it = cache.find(key);
     if (it != cache.end()) { out = it->second; return 0; }
     fpprog::Program P;
@@ -230,7 +235,7 @@ static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &ou
         for (int j = 0; j < key; j++) len[j] = ml_seg_hi(j, key) - ml_seg_lo(j, key) + 1;
         P = fpprog::build_combine(key, len);
     } else {
-        P = fpprog::build_final(key);
+        P = fpprog::build_final(key, kind == 1 ? fpprog::INV_EXTERNAL : fpprog::INV_EMIT_ARG);
     }
     if (!P.ok) return fail(ctx, BLSGPU_ERR_ARG, "tail program does not fit the slot file");
     blsgpu_ctx::dev_prog dp;
@@ -245,13 +250,13 @@ static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &ou
     return 0;
 }
 
-static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp *in0, fp *out0) {
+static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp *in0, fp *out0, const fp *in1 = nullptr) {
     size_t smem = (size_t)p.nslots * sizeof(fp);
     if (smem > 48 * 1024) {
         static bool raised = false;
         if (!raised) { CK(cudaFuncSetAttribute(k_fp_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); raised = true; }
     }
-    k_fp_program<<<1, 32, smem, ctx->stream>>>(p.d, in0, nullptr, ctx->d_consts, out0);
+    k_fp_program<<<1, 32, smem, ctx->stream>>>(p.d, in0, in1, ctx->d_consts, out0);
     ctx->launches++;
     return 0;
 }
@@ -412,10 +417,16 @@ static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_in
         k_final<<<1, 32, 0, s>>>(parts, count, d_rank_flags, ctx->d_gtb, ctx->d_flags + 1);
         ctx->launches++;
     } else {
-        blsgpu_ctx::dev_prog fpg;
-        int rc = get_prog(ctx, 1, count, fpg);
+        // norm program -> one-thread binary-Euclid inversion -> main program (fpprog.hpp build_final)
+        blsgpu_ctx::dev_prog fpn, fpg;
+        int rc = get_prog(ctx, 2, count, fpn);
+        if (!rc) rc = get_prog(ctx, 1, count, fpg);
         if (rc) return rc;
-        rc = launch_prog(ctx, fpg, (const fp *)parts, (fp *)ctx->d_gt);
+        rc = launch_prog(ctx, fpn, (const fp *)parts, ctx->d_norm);
+        if (rc) return rc;
+        k_fp_inv_one<<<1, 32, 0, s>>>(ctx->d_norm, ctx->d_norm + 1);
+        ctx->launches++;
+        rc = launch_prog(ctx, fpg, (const fp *)parts, (fp *)ctx->d_gt, ctx->d_norm + 1);
         if (rc) return rc;
         k_final_out<<<1, 32, 0, s>>>(ctx->d_gt, count, d_rank_flags, ctx->d_gtb, ctx->d_flags + 1);
         ctx->launches++;

@@ -35,6 +35,8 @@ BLS_FN bool f_eq(const fp2 &a, const fp2 &b) { return fp2_eq(a, b); }
 BLS_FN void f_set_zero(fp2 &r) { fp2_set_zero(r); }
 BLS_FN void f_set_one(fp2 &r) { r.c0 = FP_ONE; fp_set_zero(r.c1); }
 BLS_FN void f_inv(fp2 &r, const fp2 &a) { fp2_inv(r, a); }
+BLS_FN void f_inv_vt(fp &r, const fp &a) { fp_inv_vartime(r, a); }
+BLS_FN void f_inv_vt(fp2 &r, const fp2 &a) { fp2_inv_vartime(r, a); }
 
 template <class F> struct jac_t { F x, y, z; };
 template <class F> struct aff_t { F x, y; };
@@ -202,6 +204,17 @@ template <class F> BLS_NOINLINE void pt_to_affine(aff_t<F> &r, const jac_t<F> &p
     if (pt_is_inf(p)) { f_set_zero(r.x); f_set_zero(r.y); return; }
     F zi, zi2;
     f_inv(zi, p.z);
+    f_sqr(zi2, zi);
+    f_mul(r.x, p.x, zi2);
+    f_mul(zi2, zi2, zi);
+    f_mul(r.y, p.y, zi2);
+}
+
+// same through the variable-time inversion: for kernels where ONE thread normalises one public point
+template <class F> BLS_NOINLINE void pt_to_affine_vt(aff_t<F> &r, const jac_t<F> &p) {
+    if (pt_is_inf(p)) { f_set_zero(r.x); f_set_zero(r.y); return; }
+    F zi, zi2;
+    f_inv_vt(zi, p.z);
     f_sqr(zi2, zi);
     f_mul(r.x, p.x, zi2);
     f_mul(zi2, zi2, zi);

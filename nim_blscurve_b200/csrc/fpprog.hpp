@@ -109,8 +109,17 @@ inline V12 conj(V12 a) { return {a.c0, neg(a.c1)}; }
 static const uint64_t P_MINUS_2[6] = {0xb9feffffffffaaa9ull, 0x1eabfffeb153ffffull, 0x6730d2a0f6b0f624ull,
                                       0x64774b84f38512bfull, 0x4b1ba7b6434bacd7ull, 0x1a0111ea397fe69aull};
 
+// The one Fp inversion of a tail can be taken out of the dataflow program: a 444-step Fermat chain is the longest
+// serial stretch of the final exponentiation, and a single thread running the branchy binary Euclid of fpx.cuh
+// (fp_inv_vartime) is about four times quicker.  Mode 1 traces up to the inversion and emits its argument as OUT0[0]
+// (everything downstream is dead code and pruned); mode 2 reads the inverse from IN1[0].
+enum { INV_INLINE = 0, INV_EMIT_ARG = 1, INV_EXTERNAL = 2 };
+static thread_local int g_inv_mode = INV_INLINE;
+
 // 1/a = a^(p-2), fixed 4-bit windows (0 -> 0)
 inline V inv(V a) {
+    if (g_inv_mode == INV_EMIT_ARG) { g_b->output(a.id, BUF_OUT0, 0); return {g_b->leaf(BUF_IN1, 0)}; }
+    if (g_inv_mode == INV_EXTERNAL) return {g_b->leaf(BUF_IN1, 0)};
     V tbl[16];
     tbl[1] = a;
     for (int i = 2; i < 16; i++) tbl[i] = tbl[i - 1] * a;
@@ -332,10 +341,13 @@ inline Program build_combine(int nseg, const int *seg_len) {
     return compile(b);
 }
 
-// product of `count` partials (IN0: count x 12 fp) followed by the final exponentiation -> OUT0: 12 fp
-inline Program build_final(int count) {
+// product of `count` partials (IN0: count x 12 fp) followed by the final exponentiation -> OUT0: 12 fp.
+// inv_mode INV_INLINE: one self-contained program.  INV_EMIT_ARG + INV_EXTERNAL: a pair of programs around an
+// external inversion (OUT0[0] of the first = the Fp norm to invert, IN1[0] of the second = its inverse).
+inline Program build_final(int count, int inv_mode = INV_INLINE) {
     Builder b;
     g_b = &b;
+    g_inv_mode = inv_mode;
     std::vector<V12> v;
     for (int i = 0; i < count; i++) v.push_back(load12(BUF_IN0, 12 * i));
     while (v.size() > 1) {                                  // balanced product tree
@@ -344,7 +356,66 @@ inline Program build_final(int count) {
         if (v.size() & 1) w.push_back(v.back());
         v.swap(w);
     }
-    store12(final_exp(v[0]), BUF_OUT0, 0);
+    V12 r = final_exp(v[0]);
+    if (inv_mode != INV_EMIT_ARG) store12(r, BUF_OUT0, 0);
+    g_inv_mode = INV_INLINE;
+    g_b = nullptr;
+    return compile(b);
+}
+
+// ---- G1 in homogeneous projective coordinates, complete formulas --------------------------------------------------
+// Renes-Costello-Batina (2016) algorithms 7 and 9 for y^2 = x^3 + b with a = 0, b = 4 (b3 = 12).  E(Fp) has odd order
+// (cofactor (z-1)^2/3 and r are odd), so the formulas have no exceptional inputs: infinity is (0 : y : 0), P + P,
+// P - P and P + infinity all come out of the same straight line — which is what a branch-free dataflow program needs.
+// The point carries N = 2Z and M = 6Z so that the doubling needs no constant multiplications and only shallow
+// addition chains between its two multiplication levels (12 Z^2 = M N, 36 Z^2 = M^2, 8 Y^2 Y Z = 4 Y^2 (Y N)).
+struct VP { V x, y, z, n, m; };
+inline VP vp_make(V x, V y, V z) {
+    V n = z + z, n2 = n + n;
+    return {x, y, z, n, n2 + n};
+}
+inline VP rcb_dbl(VP p) {
+    V A = p.y * p.y, B2 = p.y * p.n, D = p.x * p.y, E36 = p.m * p.m, E12 = p.m * p.n;
+    V t0 = A - E36, ys = A + E12;
+    V A2 = A + A, A4 = A2 + A2, A8 = A4 + A4;
+    V xh = D * t0, yp = t0 * ys, yq = A8 * E12, z3 = A4 * B2, n3 = A8 * B2;
+    V n6 = n3 + n3;
+    return {xh + xh, yp + yq, z3, n3, n6 + n3};
+}
+inline V mul12(V a) {
+    V a2 = a + a, a4 = a2 + a2, a8 = a4 + a4;
+    return a8 + a4;
+}
+inline VP rcb_add(VP p, VP q) {
+    V t0 = p.x * q.x, t1 = p.y * q.y, t2 = p.z * q.z;
+    V t3 = (p.x + p.y) * (q.x + q.y) - (t0 + t1);
+    V t4 = (p.y + p.z) * (q.y + q.z) - (t1 + t2);
+    V y3 = (p.x + p.z) * (q.x + q.z) - (t0 + t2);
+    V t0x3 = t0 + t0 + t0;
+    V t2b = mul12(t2);
+    V z3 = t1 + t2b, t1m = t1 - t2b;
+    V y3b = mul12(y3);
+    V x3 = t3 * t1m - t4 * y3b;
+    V yy = y3b * t0x3 + t1m * z3;
+    V zz = z3 * t4 + t0x3 * t3;
+    return vp_make(x3, yy, zz);
+}
+
+// Horner over the window sums of a G1 MSM (multi_scalar.c:295-311 integrates and combines windows the same way):
+// IN0 = nwin homogeneous points (3 fp each, window 0 first; infinity as (0, 1, 0)), acc = [2^c] acc + W_w from the top
+// window down.  OUT0[0..2] = the homogeneous result (X : Y : Z); the caller normalises it (one inversion).
+inline Program build_msm_horner_g1(int nwin, int c) {
+    Builder b;
+    g_b = &b;
+    auto load = [&](int w) { return vp_make({b.leaf(BUF_IN0, 3 * w)}, {b.leaf(BUF_IN0, 3 * w + 1)}, {b.leaf(BUF_IN0, 3 * w + 2)}); };
+    VP acc = load(nwin - 1);
+    for (int w = nwin - 2; w >= 0; w--) {
+        for (int k = 0; k < c; k++) acc = rcb_dbl(acc);
+        acc = rcb_add(acc, load(w));
+    }
+    b.output(acc.x.id, BUF_OUT0, 0);
+    b.output(acc.y.id, BUF_OUT0, 1);
+    b.output(acc.z.id, BUF_OUT0, 2);
     g_b = nullptr;
     return compile(b);
 }

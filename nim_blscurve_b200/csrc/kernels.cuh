@@ -238,7 +238,7 @@ __global__ void k_sig_pair(const g2_jac *S, size_t n, g2_aff *Q, g1_aff *P) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     g2_jac s = *S;
     g2_aff sa;
-    pt_to_affine(sa, s);                                 // S = infinity -> all-zero -> neutral lines
+    pt_to_affine_vt(sa, s);                              // S = infinity -> all-zero -> neutral lines
     Q[n] = sa;
     g1_aff g;
     g.x = G1_GEN_X;
@@ -447,6 +447,14 @@ __global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const f
     for (uint32_t e = lane; e < nout; e += 32) out0[op[2 * e + 1] & 0xffffffu] = slots[op[2 * e]];
 }
 
+// the Fp inversion lifted out of the final-exponentiation program (fpprog.hpp INV_EXTERNAL): one thread, binary Euclid
+__global__ void k_fp_inv_one(const fp *in, fp *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    fp a = *in, r;
+    fp_inv_vartime(r, a);
+    *out = r;
+}
+
 // verdict and canonical GT bytes of the final exponentiation result (fp12_tower.c:773-786): 12 lanes, one Fp each
 __global__ void k_final_out(const fp12 *gt, int count, const int *flags, uint8_t *gt_bytes, int *is_one) {
     const int t = threadIdx.x;
@@ -606,14 +614,14 @@ __global__ void k_g1_to_affine(const g1_jac *in, g1_aff *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     g1_jac j = *in;
     g1_aff a;
-    pt_to_affine(a, j);
+    pt_to_affine_vt(a, j);
     *out = a;
 }
 __global__ void k_g2_to_affine(const g2_jac *in, g2_aff *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     g2_jac j = *in;
     g2_aff a;
-    pt_to_affine(a, j);
+    pt_to_affine_vt(a, j);
     *out = a;
 }
 

@@ -20,8 +20,12 @@
 // multiplication at a time.
 // Scalars are NOT reduced mod r (as in the reference); the nbits low bits of each little-endian scalar are used.
 #pragma once
+#include <cstdlib>
+#include <map>
 #include <string>
+#include <type_traits>
 #include "kernels.cuh"
+#include "fpprog.hpp"
 
 namespace bls {
 
@@ -29,9 +33,20 @@ struct msm_state {
     uint8_t *buf = nullptr;
     size_t bytes = 0;
     int sms = 148;                 // SM count of the device (B200: 148); set at context creation
+    // window-group pipelining: the latency-bound tail of a group (combine, segment, tree, Horner) runs on this
+    // higher-priority stream underneath the bucket accumulation of the next group
+    struct horner_prog { uint32_t *d = nullptr; int nslots = 0; };
+    std::map<int, horner_prog> horner;      // G1 window-Horner dataflow programs (fpprog.hpp), keyed by nwin * 64 + c
+    cudaStream_t tail = nullptr;
+    cudaEvent_t ev_group[8] = {}, ev_done = nullptr;
+    bool ev_ok = false;
 };
 
 static inline void msm_free(msm_state &m) {
+    if (m.ev_ok) { for (int i = 0; i < 8; i++) cudaEventDestroy(m.ev_group[i]); cudaEventDestroy(m.ev_done); m.ev_ok = false; }
+    if (m.tail) { cudaStreamDestroy(m.tail); m.tail = nullptr; }
+    for (auto &kv : m.horner) cudaFree(kv.second.d);
+    m.horner.clear();
     if (m.buf) cudaFree(m.buf);
     m.buf = nullptr;
     m.bytes = 0;
@@ -164,12 +179,13 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *scalars, siz
 // its entries touch.
 template <class F>
 __global__ void BLS_LB k_msm_chunks(const uint8_t *points, size_t pstride, const uint32_t *offsets, const uint32_t *rank,
-                                    const uint32_t *entries, size_t nb, uint32_t K, jac_t<F> *partials) {
+                                    const uint32_t *entries, size_t b0, size_t b1, uint32_t K, jac_t<F> *partials) {
+    // window group = buckets [b0, b1): its entries are [S, E); chunks, partial slots and ranks are group-relative
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t E = offsets[nb];
-    if (t * K >= E) return;
-    const uint32_t e0 = (uint32_t)(t * K), e1 = E - e0 > K ? e0 + K : E;
-    size_t lo = 0, hi = nb;                        // largest b with offsets[b] <= e0: the (non-empty) bucket of entry e0
+    const uint32_t S = offsets[b0], E = offsets[b1], rank0 = rank[b0];
+    if (t * K >= (size_t)(E - S)) return;
+    const uint32_t e0 = S + (uint32_t)(t * K), e1 = E - e0 > K ? e0 + K : E;
+    size_t lo = b0, hi = b1;                       // largest b with offsets[b] <= e0: the (non-empty) bucket of entry e0
     while (hi - lo > 1) {
         size_t mid = (lo + hi) >> 1;
         if (offsets[mid] <= e0) lo = mid; else hi = mid;
@@ -180,7 +196,7 @@ __global__ void BLS_LB k_msm_chunks(const uint8_t *points, size_t pstride, const
     pt_set_inf(acc);
     for (uint32_t e = e0; e < e1; e++) {
         if (e == bend) {                           // bucket boundary: flush the run, move to the next non-empty bucket
-            partials[t + rank[b]] = acc;
+            partials[t + (rank[b] - rank0)] = acc;
             pt_set_inf(acc);
             do { b++; bend = offsets[b + 1]; } while (bend <= e);
         }
@@ -189,28 +205,28 @@ __global__ void BLS_LB k_msm_chunks(const uint8_t *points, size_t pstride, const
         if (ent & 1) f_neg(p.y, p.y);
         pt_add_affine(acc, acc, p);
     }
-    partials[t + rank[b]] = acc;
+    partials[t + (rank[b] - rank0)] = acc;
 }
 
 // partial slots of bucket b (count > 0): [base, base + np)
 __device__ __forceinline__ void msm_bucket_slots(const uint32_t *offsets, const uint32_t *rank, size_t b, uint32_t K,
-                                                 uint32_t &base, uint32_t &np) {
+                                                 uint32_t S, uint32_t rank0, uint32_t &base, uint32_t &np) {
     const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
     if (o1 == o0) { base = 0; np = 0; return; }
-    const uint32_t t0 = o0 / K, t1 = (o1 - 1) / K;
-    base = t0 + rank[b];
+    const uint32_t t0 = (o0 - S) / K, t1 = (o1 - 1 - S) / K;
+    base = t0 + (rank[b] - rank0);
     np = t1 - t0 + 1;
 }
 
 template <class F>
-__global__ void BLS_LB k_msm_combine(const jac_t<F> *partials, const uint32_t *offsets, const uint32_t *rank, size_t nb,
-                                     uint32_t K, jac_t<F> *buckets, uint32_t *biglist, uint32_t *bigcount) {
-    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
+__global__ void BLS_LB k_msm_combine(const jac_t<F> *partials, const uint32_t *offsets, const uint32_t *rank, size_t b0,
+                                     size_t b1, uint32_t K, jac_t<F> *buckets, uint32_t *biglist, uint32_t *bigcount) {
+    size_t b = b0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= b1) return;
     uint32_t base, np;
-    msm_bucket_slots(offsets, rank, b, K, base, np);
+    msm_bucket_slots(offsets, rank, b, K, offsets[b0], rank[b0], base, np);
     if (np > MSM_BIG) {
-        biglist[atomicAdd(bigcount, 1u)] = (uint32_t)b;
+        biglist[b0 + atomicAdd(bigcount, 1u)] = (uint32_t)b;
         return;
     }
     jac_t<F> acc;
@@ -225,15 +241,15 @@ __global__ void BLS_LB k_msm_combine(const jac_t<F> *partials, const uint32_t *o
 
 // one warp per over-full bucket: lanes stride over its partials, then a shuffle tree
 template <class F>
-__global__ void BLS_LB k_msm_combine_big(const jac_t<F> *partials, const uint32_t *offsets, const uint32_t *rank, uint32_t K,
-                                         const uint32_t *biglist, const uint32_t *bigcount, jac_t<F> *buckets) {
+__global__ void BLS_LB k_msm_combine_big(const jac_t<F> *partials, const uint32_t *offsets, const uint32_t *rank, size_t b0,
+                                         uint32_t K, const uint32_t *biglist, const uint32_t *bigcount, jac_t<F> *buckets) {
     const int lane = threadIdx.x & 31;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t nbig = *bigcount;
     for (size_t i = warp; i < nbig; i += nwarps) {
-        const uint32_t b = biglist[i];
+        const uint32_t b = biglist[b0 + i];
         uint32_t base, np;
-        msm_bucket_slots(offsets, rank, b, K, base, np);
+        msm_bucket_slots(offsets, rank, b, K, offsets[b0], rank[b0], base, np);
         jac_t<F> acc;
         pt_set_inf(acc);
         for (uint32_t t = lane; t < np; t += 32) {
@@ -290,19 +306,64 @@ __global__ void BLS_LB k_tree_rows(jac_t<F> *S, int rows, size_t stride, size_t 
     S[r * stride + i] = a;
 }
 
+// Horner over the windows of one group, top window first: acc = [2^c] acc + W_w.  `carry` holds the running value
+// across groups (read unless `first`, written unless this is the last group, which emits the result instead).
 template <class F>
-__global__ void k_msm_horner(const jac_t<F> *W, size_t stride, int nwin, int c, jac_t<F> *out_jac, aff_t<F> *out_aff) {
+__global__ void k_msm_horner(const jac_t<F> *W, size_t stride, int nwin, int c, int first, int last, jac_t<F> *carry,
+                             jac_t<F> *out_jac, aff_t<F> *out_aff) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    jac_t<F> acc = W[(size_t)(nwin - 1) * stride];
-    for (int w = nwin - 2; w >= 0; w--) {
+    jac_t<F> acc;
+    int w = nwin - 1;
+    if (first) { acc = W[(size_t)w * stride]; w--; } else acc = *carry;
+    for (; w >= 0; w--) {
         for (int k = 0; k < c; k++) pt_dbl(acc, acc);
         jac_t<F> x = W[(size_t)w * stride];
         pt_add(acc, acc, x);
     }
+    if (!last) { *carry = acc; return; }
     if (out_jac) *out_jac = acc;
     if (out_aff) {
         aff_t<F> a;
-        pt_to_affine(a, acc);
+        pt_to_affine_vt(a, acc);
+        *out_aff = a;
+    }
+}
+
+// G1 window Horner as a warp-cooperative dataflow program (fpprog.hpp build_msm_horner_g1, run by k_fp_program):
+// the 255 sequential doublings cost two multiplication levels each instead of seven dependent multiplications.
+// prep: window sums, Jacobian (X, Y, Z) -> homogeneous (X Z : Y : Z^3), infinity -> (0 : 1 : 0)
+__global__ void k_msm_horner_prep(const g1_jac *W, size_t stride, int nwin, fp *hom) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwin) return;
+    g1_jac p = W[(size_t)w * stride];
+    fp x, y, z;
+    if (pt_is_inf(p)) {
+        fp_set_zero(x); y = FP_ONE; fp_set_zero(z);
+    } else {
+        fp z2;
+        fp_mul_ni(x, p.x, p.z);
+        y = p.y;
+        fp_sqr_ni(z2, p.z);
+        fp_mul_ni(z, z2, p.z);
+    }
+    hom[3 * w] = x; hom[3 * w + 1] = y; hom[3 * w + 2] = z;
+}
+// finish: homogeneous (X : Y : Z) -> affine (X/Z, Y/Z) and/or Jacobian (X Z, Y Z^2, Z); infinity -> all zero
+__global__ void k_msm_horner_finish(const fp *hom, g1_jac *out_jac, g1_aff *out_aff) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    fp X = hom[0], Y = hom[1], Z = hom[2];
+    if (out_jac) {
+        g1_jac j;
+        if (fp_is_zero(Z)) pt_set_inf(j);
+        else { fp z2; fp_mul_ni(j.x, X, Z); fp_sqr_ni(z2, Z); fp_mul_ni(j.y, Y, z2); j.z = Z; }
+        *out_jac = j;
+    }
+    if (out_aff) {
+        g1_aff a;
+        fp zi;
+        fp_inv_vartime(zi, Z);
+        fp_mul_ni(a.x, X, zi);
+        fp_mul_ni(a.y, Y, zi);
         *out_aff = a;
     }
 }
@@ -359,22 +420,41 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
     msm_shape(n, nbits, c, nwin);
     const size_t B = (size_t)1 << (c - 1);
     const size_t nb = (size_t)nwin * B;
-    // entries per chunk: the chunk grid fills whole waves of the resident-thread capacity (SMs x 4 blocks x 128) with
-    // about 32 additions per thread; short MSMs get one wave of shorter chunks
     const size_t emax = n * (size_t)nwin;
     const size_t wave = (size_t)st.sms * BLS_LB_BLOCKS * 128;
-    size_t waves = emax / (wave * 32);
-    if (waves < 1) waves = 1;
-    size_t Kz = (emax + waves * wave - 1) / (waves * wave);
-    if (Kz < 8) Kz = 8;
-    const uint32_t K = (uint32_t)Kz;
     size_t L = B / 512;                            // segment length: short serial chains, <= 512 segments per window
     if (L < 4) L = 4;
     if (L > 32) L = 32;
+    static const int l_env = getenv("BLSGPU_MSM_L") ? atoi(getenv("BLSGPU_MSM_L")) : 0;
+    if (l_env > 0) L = (size_t)l_env;
     if (L > B) L = B;
     const size_t nseg = B / L;
-    const size_t nchunks = (emax + K - 1) / K;
-    const size_t pmax = nchunks + nb + 1;          // partial slots: chunk index + rank of the bucket
+    // Window groups, top windows first.  The tail of a group is latency-bound (a few thousand threads, then one), so
+    // it runs on the tail stream while the main stream accumulates the buckets of the next group.
+    static const int g_env = getenv("BLSGPU_MSM_GROUPS") ? atoi(getenv("BLSGPU_MSM_GROUPS")) : 0;
+    int G = g_env > 0 ? g_env : 1;
+    if (G > 8) G = 8;
+    if (G > nwin) G = nwin;
+    int gw0[9];                                    // group g = windows [gw0[g+1], gw0[g]) counted from the top
+    gw0[0] = nwin;
+    for (int g = 0; g < G; g++) gw0[g + 1] = nwin - (int)(((size_t)nwin * (g + 1)) / G);
+    // entries per chunk, per group: the chunk grid of a group fills whole waves of the resident-thread capacity
+    // (SMs x 4 blocks x 128) with about 32 additions per thread; short MSMs get one wave of shorter chunks
+    uint32_t Kg[8];
+    size_t preg[9];                                // partial-slot regions: chunks of the group + its buckets + 1
+    preg[0] = 0;
+    for (int g = 0; g < G; g++) {
+        const size_t wg = (size_t)(gw0[g] - gw0[g + 1]), eg = n * wg;
+        size_t waves = eg / (wave * 32);
+        if (waves < 1) waves = 1;
+        size_t Kz = (eg + waves * wave - 1) / (waves * wave);
+        if (Kz < 8) Kz = 8;
+        static const int k_env = getenv("BLSGPU_MSM_K") ? atoi(getenv("BLSGPU_MSM_K")) : 0;
+        if (k_env > 0) Kz = (size_t)k_env;
+        Kg[g] = (uint32_t)Kz;
+        preg[g + 1] = preg[g] + (eg + Kz - 1) / Kz + 1 + wg * B + 1;
+    }
+    const size_t pmax = preg[G];
     const size_t nsb = (nb + 1023) / 1024;         // scan blocks
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o_counts = 0;
@@ -384,7 +464,9 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
     size_t o_bsums = o_rank + al((nb + 1) * 4);
     size_t o_big = o_bsums + al(nsb * 8);
     size_t o_bigcount = o_big + al(nb * 4);
-    size_t o_entries = o_bigcount + 256;
+    size_t o_carry = o_bigcount + 256;
+    size_t o_hom = o_carry + al(sizeof(J));
+    size_t o_entries = o_hom + al((size_t)(3 * nwin + 3) * 48);
     size_t o_partials = o_entries + al(emax * 4);
     size_t o_buckets = o_partials + al(pmax * sizeof(J));
     size_t o_segs = o_buckets + al(nb * sizeof(J));
@@ -392,11 +474,19 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
     cudaError_t e;
 #define MCK(call) if ((e = (call)) != cudaSuccess) { err = std::string(#call ": ") + cudaGetErrorString(e); return -1; }
     if (st.bytes < total) {
-        if (st.buf) { MCK(cudaStreamSynchronize(s)); cudaFree(st.buf); }
+        if (st.buf) { MCK(cudaStreamSynchronize(s)); if (st.tail) MCK(cudaStreamSynchronize(st.tail)); cudaFree(st.buf); }
         st.buf = nullptr;
         st.bytes = 0;
         MCK(cudaMalloc((void **)&st.buf, total));
         st.bytes = total;
+    }
+    if (G > 1 && !st.tail) {
+        int lo_pri = 0, hi_pri = 0;
+        MCK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        MCK(cudaStreamCreateWithPriority(&st.tail, cudaStreamNonBlocking, hi_pri));
+        for (int i = 0; i < 8; i++) MCK(cudaEventCreateWithFlags(&st.ev_group[i], cudaEventDisableTiming));
+        MCK(cudaEventCreateWithFlags(&st.ev_done, cudaEventDisableTiming));
+        st.ev_ok = true;
     }
     uint32_t *counts = (uint32_t *)(st.buf + o_counts), *offsets = (uint32_t *)(st.buf + o_offsets);
     uint32_t *cursor = (uint32_t *)(st.buf + o_cursor), *rank = (uint32_t *)(st.buf + o_rank);
@@ -404,28 +494,77 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
     uint32_t *biglist = (uint32_t *)(st.buf + o_big), *bigcount = (uint32_t *)(st.buf + o_bigcount);
     uint32_t *entries = (uint32_t *)(st.buf + o_entries);
     J *partials = (J *)(st.buf + o_partials), *buckets = (J *)(st.buf + o_buckets), *segs = (J *)(st.buf + o_segs);
+    J *carry = (J *)(st.buf + o_carry);
     MCK(cudaMemsetAsync(counts, 0, nb * 4, s));
-    MCK(cudaMemsetAsync(bigcount, 0, 4, s));
+    MCK(cudaMemsetAsync(bigcount, 0, 4 * 8, s));
     int nl = 0;
     k_msm_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, sstride, n, sb, nbits, c, nwin, counts);
     k_msm_scan_blocks<<<(unsigned)nsb, 1024, 0, s>>>(counts, nb, bsums);
     k_msm_scan_top<<<1, 1024, 0, s>>>(bsums, nsb);
     k_msm_scan_apply<<<(unsigned)nsb, 1024, 0, s>>>(counts, nb, bsums, offsets, cursor, rank);
     k_msm_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, sstride, n, sb, nbits, c, nwin, cursor, entries);
-    k_msm_chunks<F><<<(unsigned)((nchunks + 127) / 128), 128, 0, s>>>(d_points, pstride, offsets, rank, entries, nb, K, partials);
-    k_msm_combine<F><<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(partials, offsets, rank, nb, K, buckets, biglist, bigcount);
-    k_msm_combine_big<F><<<64, 128, 0, s>>>(partials, offsets, rank, K, biglist, bigcount, buckets);
-    size_t nt = (size_t)nwin * nseg;
-    k_msm_segment<F><<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(buckets, c, nwin, (uint32_t)L, segs);
-    nl += 9;
-    for (size_t m = nseg; m > 1;) {
-        size_t half = (m + 1) / 2;
-        k_tree_rows<F><<<(unsigned)(((size_t)nwin * half + 127) / 128), 128, 0, s>>>(segs, nwin, nseg, m, half);
-        nl++;
-        m = half;
+    nl += 5;
+    for (int g = 0; g < G; g++) {
+        const int w0 = gw0[g + 1], wg = gw0[g] - gw0[g + 1];
+        const size_t b0 = (size_t)w0 * B, b1 = b0 + (size_t)wg * B;
+        const uint32_t K = Kg[g];
+        const size_t gchunks = (n * (size_t)wg + K - 1) / K + 1;
+        J *pg = partials + preg[g];
+        k_msm_chunks<F><<<(unsigned)((gchunks + 127) / 128), 128, 0, s>>>(d_points, pstride, offsets, rank, entries, b0, b1, K, pg);
+        cudaStream_t ts = s;
+        if (G > 1) {
+            MCK(cudaEventRecord(st.ev_group[g], s));
+            MCK(cudaStreamWaitEvent(st.tail, st.ev_group[g], 0));
+            ts = st.tail;
+        }
+        k_msm_combine<F><<<(unsigned)(((size_t)wg * B + 127) / 128), 128, 0, ts>>>(pg, offsets, rank, b0, b1, K, buckets, biglist, bigcount + g);
+        k_msm_combine_big<F><<<64, 128, 0, ts>>>(pg, offsets, rank, b0, K, biglist, bigcount + g, buckets);
+        size_t nt = (size_t)wg * nseg;
+        J *sg = segs + (size_t)w0 * nseg;
+        k_msm_segment<F><<<(unsigned)((nt + 127) / 128), 128, 0, ts>>>(buckets + b0, c, wg, (uint32_t)L, sg);
+        nl += 4;
+        for (size_t m = nseg; m > 1;) {
+            size_t half = (m + 1) / 2;
+            k_tree_rows<F><<<(unsigned)(((size_t)wg * half + 127) / 128), 128, 0, ts>>>(sg, wg, nseg, m, half);
+            nl++;
+            m = half;
+        }
+        bool programmed = false;
+        if constexpr (std::is_same<F, fp>::value) {
+            static const bool prog_env = !(getenv("BLSGPU_MSM_HORNER_PROG") && atoi(getenv("BLSGPU_MSM_HORNER_PROG")) == 0);
+            if (G == 1 && nwin <= 128 && prog_env) {
+                msm_state::horner_prog hp;
+                auto it = st.horner.find(nwin * 64 + c);
+                if (it != st.horner.end()) hp = it->second;
+                else {
+                    fpprog::Program P = fpprog::build_msm_horner_g1(nwin, c);
+                    if (P.ok && (size_t)P.nslots * sizeof(fp) <= 48 * 1024) {
+                        MCK(cudaMalloc((void **)&hp.d, P.words.size() * 4));
+                        MCK(cudaMemcpyAsync(hp.d, P.words.data(), P.words.size() * 4, cudaMemcpyHostToDevice, s));
+                        MCK(cudaStreamSynchronize(s));       // first use of this shape only: the host vector goes away
+                        hp.nslots = P.nslots;
+                    }
+                    st.horner[nwin * 64 + c] = hp;
+                }
+                if (hp.d) {
+                    fp *hom = (fp *)(st.buf + o_hom);
+                    k_msm_horner_prep<<<1, 128, 0, ts>>>(sg, nseg, nwin, hom);
+                    k_fp_program<<<1, 32, (size_t)hp.nslots * sizeof(fp), ts>>>(hp.d, hom, nullptr, nullptr, hom + 3 * nwin);
+                    k_msm_horner_finish<<<1, 32, 0, ts>>>(hom + 3 * nwin, d_out_jac, d_out_aff);
+                    nl += 3;
+                    programmed = true;
+                }
+            }
+        }
+        if (!programmed) {
+            k_msm_horner<F><<<1, 32, 0, ts>>>(sg, nseg, wg, c, g == 0, g == G - 1, carry, d_out_jac, d_out_aff);
+            nl++;
+        }
     }
-    k_msm_horner<F><<<1, 32, 0, s>>>(segs, nseg, nwin, c, d_out_jac, d_out_aff);
-    nl++;
+    if (G > 1) {
+        MCK(cudaEventRecord(st.ev_done, st.tail));
+        MCK(cudaStreamWaitEvent(s, st.ev_done, 0));
+    }
     MCK(cudaGetLastError());
 #undef MCK
     if (launches) *launches += nl;

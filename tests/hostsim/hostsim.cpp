@@ -17,6 +17,7 @@ void hs_fp_mul(const fp *a, const fp *b, fp *r) { fp_mul(*r, *a, *b); }
 void hs_fp_add(const fp *a, const fp *b, fp *r) { fp_add(*r, *a, *b); }
 void hs_fp_sub(const fp *a, const fp *b, fp *r) { fp_sub(*r, *a, *b); }
 void hs_fp_inv(const fp *a, fp *r) { fp_inv(*r, *a); }
+void hs_fp_inv_vartime(const fp *a, fp *r) { fp_inv_vartime(*r, *a); }
 int hs_fp2_rsqrt(const fp2 *a, fp2 *r) { return fp2_rsqrt_or_z(*r, *a) ? 1 : 0; }
 void hs_hash_to_g2(const uint8_t *msg, size_t len, const uint8_t *dst, uint32_t dst_len, g2_aff *aff, uint8_t *comp) {
     g2_jac j;
@@ -136,6 +137,19 @@ int hs_prog_final(const fp12 *partials, int count, fp12 *out, int *stats) {
     stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
     return 1;
 }
+// the device path: norm program -> fp_inv_vartime -> main program reading the inverse from IN1
+int hs_prog_final_split(const fp12 *partials, int count, fp12 *out, int *stats) {
+    fpprog::Program A = fpprog::build_final(count, fpprog::INV_EMIT_ARG), B = fpprog::build_final(count, fpprog::INV_EXTERNAL);
+    if (!A.ok || !B.ok) return 0;
+    fp cst[fpprog::CONST_COUNT];
+    const_pool(cst);
+    fp norm, ninv;
+    run_program(A.words, (const fp *)partials, nullptr, cst, &norm);
+    fp_inv_vartime(ninv, norm);
+    run_program(B.words, (const fp *)partials, &ninv, cst, (fp *)out);
+    stats[0] = A.nrounds + B.nrounds; stats[1] = A.nmul_rounds + B.nmul_rounds; stats[2] = B.nslots; stats[3] = A.nops + B.nops;
+    return 1;
+}
 int hs_prog_combine(const fp12 *seg, int nseg, fp12 *out, int *stats) {
     int len[64];
     for (int j = 0; j < nseg; j++) len[j] = ml_seg_hi(j, nseg) - ml_seg_lo(j, nseg) + 1;
@@ -144,6 +158,14 @@ int hs_prog_combine(const fp12 *seg, int nseg, fp12 *out, int *stats) {
     fp cst[fpprog::CONST_COUNT];
     const_pool(cst);
     run_program(P.words, (const fp *)seg, nullptr, cst, (fp *)out);
+    stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
+    return 1;
+}
+// G1 MSM window Horner as a dataflow program: hom = nwin x (X, Y, Z) homogeneous, out = (X, Y, Z) homogeneous
+int hs_prog_msm_horner(const fp *hom, int nwin, int c, fp *out5, int *stats) {
+    fpprog::Program P = fpprog::build_msm_horner_g1(nwin, c);
+    if (!P.ok) return 0;
+    run_program(P.words, hom, nullptr, nullptr, out5);
     stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
     return 1;
 }

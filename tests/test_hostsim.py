@@ -56,6 +56,11 @@ def test_fp_ops(hs):
         r = out(48)
         hs.hs_fp_inv(buf(pr.fp_to_mont_bytes(a)), r)
         assert pr.fp_from_mont_bytes(bytes(r)) == pr.inv(a)
+    # binary extended Euclid (single-thread tails): same inverse, 0 -> 0
+    for a in [0, 1, 2, P - 1, P - 2, (P - 1) // 2, 1 << 380, (1 << 381) - 1] + [rng.randrange(1, P) for _ in range(200)]:
+        r = out(48)
+        hs.hs_fp_inv_vartime(buf(pr.fp_to_mont_bytes(a)), r)
+        assert pr.fp_from_mont_bytes(bytes(r)) == (pr.inv(a) if a else 0), hex(a)
 
 
 def f2b(a):
@@ -178,12 +183,57 @@ def test_tail_programs(hs):
             prod = pr.f12_mul(prod, x)
         assert f12f(bytes(r)) == pr.final_exp(prod), count
         assert stats[2] <= 1024 and stats[1] < 1400, list(stats)
+        r2 = out(576)                           # the pair of programs around the external inversion (device path)
+        assert hs.hs_prog_final_split(buf(b"".join(f12b(x) for x in parts)), count, r2, stats) == 1
+        assert bytes(r2) == bytes(r), count
+        assert stats[2] <= 1024 and stats[1] < 950, list(stats)
     for nseg in (1, 2, 8, 21, 63):
         segs = b"".join(f12b(rnd12()) for _ in range(nseg))
         r, r2 = out(576), out(576)
         assert hs.hs_prog_combine(buf(segs), nseg, r, stats) == 1
         hs.hs_miller_combine(buf(segs), nseg, r2)
         assert bytes(r) == bytes(r2), nseg
+
+
+def test_msm_horner_program(hs):
+    """fpprog.hpp build_msm_horner_g1: the window Horner of the G1 MSM as a branch-free dataflow program over complete
+    projective formulas == sum_w [2^(c w)] W_w computed by pyref, including infinite windows, equal and opposite
+    points (the cases the Jacobian formulas of ec.cuh branch on)."""
+    rng = random.Random(21)
+    g = pr.G1_GEN
+    stats = (C.c_int * 4)()
+
+    def hom(pt):
+        if pt is None:
+            return (0, 1, 0)
+        k = rng.randrange(1, P)
+        return (pt[0] * k % P, pt[1] * k % P, k)
+    cases = []
+    for nwin, c in ((1, 5), (2, 3), (5, 13), (16, 16), (22, 12)):
+        cases.append((nwin, c, [pr.g1_mul(g, rng.randrange(1, 1 << 64)) for _ in range(nwin)]))
+    cases.append((4, 2, [None, None, None, None]))
+    cases.append((4, 2, [pr.g1_mul(g, 7), None, None, None]))
+    cases.append((3, 4, [None, pr.g1_mul(g, 5), None]))
+    q = pr.g1_mul(g, 12345)
+    cases.append((2, 1, [pr.g1_mul(q, 2), q]))                 # [2]q + [2]q: the addition must double
+    cases.append((2, 1, [pr.g1_neg(pr.g1_mul(q, 2)), q]))      # [2]q - [2]q = infinity
+    cases.append((3, 1, [q, pr.g1_neg(pr.g1_mul(q, 2)), q]))   # hits infinity in the middle, then adds again
+    for nwin, c, ws in cases:
+        exp = None
+        for w in range(nwin - 1, -1, -1):
+            if w != nwin - 1:
+                exp = pr.g1_mul(exp, 1 << c) if exp is not None else None
+            exp = pr.g1_add(exp, ws[w])
+        inp = b"".join(pr.fp_to_mont_bytes(v) for pt in ws for v in hom(pt))
+        r = out(3 * 48)
+        assert hs.hs_prog_msm_horner(buf(inp), nwin, c, r, stats) == 1
+        o = [pr.fp_from_mont_bytes(bytes(r)[48 * i:48 * i + 48]) for i in range(3)]
+        if exp is None:
+            assert o[2] == 0 and o[1] != 0, (nwin, c)
+        else:
+            zi = pr.inv(o[2])
+            assert (o[0] * zi % P, o[1] * zi % P) == exp, (nwin, c)
+        assert stats[2] <= 1024, list(stats)
 
 
 def test_g1_mul_windowed(hs):
