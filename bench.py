@@ -34,6 +34,9 @@ IMAD_PER_FPMUL = 300
 # reference-algorithm Fp-mul per set of each stage: A3, A5 (G1), A4, and A7 split into its line
 # evaluations (63 x (25+4) + 5 x (35+4)) and its accumulation (68 x 39 + shared squarings)
 STAGE_FPMUL = {"hash_to_g2": 4919, "g1_mul64": 800, "pairs_affine": 23, "miller_lines": 2022, "miller_acc": 2933}
+# algorithmic bytes per set moved by each stage's kernel (inputs read + outputs written)
+STAGE_IO_BYTES = {"hash_to_g2": 32 + 288, "g1_mul64": 96 + 8 + 144, "miller_lines": 192 + 96 + 68 * 288,
+                  "miller_acc": 68 * 288 + 576 // 8}
 
 
 def clocks_sampler(stop, out, gpu_index):
@@ -155,6 +158,27 @@ def bench_msm(L, h, cache, stream, flush, peak_wide, hbm_peak, args):
         except Exception as ex:
             res["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
     return res
+
+
+STAGE_KERNEL = {"hash_to_g2": "k_hash_sets", "miller_lines": "k_miller_lines", "miller_acc": "k_miller_acc_team",
+                "g1_mul64": "k_g1_mul"}
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes (read + write) of one launch of `kernel` from the committed `ncu --set full` capture of the same
+    workload (profiles/r1/r1_raw_pick_<kernel>.txt, written by tools/gpu_profile.sh + tools/ncu_raw_pick.py)."""
+    path = os.path.join(ROOT, "profiles", "r1", "r1_raw_pick_%s.txt" % kernel)
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot, seen = 0.0, 0
+    try:
+        for ln in open(path):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1].replace(",", "")) * mult.get(f[2], 1.0)
+                seen += 1
+    except OSError:
+        return None, None
+    return (tot, os.path.relpath(path, ROOT)) if seen == 2 else (None, None)
 
 
 def main():
@@ -294,9 +318,14 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic, traffic_src = ncu_traffic(STAGE_KERNEL.get(dom, dom))
         extra["roofline"] = {
             "bound": "int_mul_pipe", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_wide / 1e9,
-            "unit": "G IMAD.WIDE/s", "frac": achieved / peak_wide, "traffic": None,
+            "unit": "G IMAD.WIDE/s", "frac": achieved / peak_wide, "traffic": traffic,
+            "traffic_note": "DRAM bytes read+written per launch of %s, ncu --set full on the same 131072-set workload (%s); "
+                            "algorithmic bytes per launch are %d (inputs + outputs) - the rest is per-thread stack "
+                            "(local memory) traffic that overflows L2" % (STAGE_KERNEL.get(dom, dom), traffic_src,
+                                                                          S * STAGE_IO_BYTES.get(dom, 320)),
             "kernel_ms": dom_ms, "algorithmic_fpmul_per_set": STAGE_FPMUL[dom], "imad_per_fpmul": IMAD_PER_FPMUL,
             "peak_source": "k_imad_peak microbenchmark in this run (mad.wide.u32); mad.lo.u32 peak %.1f G/s" % (peak_lo / 1e9),
             "whole_step_frac": whole / peak_wide,

@@ -239,20 +239,22 @@ __global__ void BLS_LB k_msm_combine(const jac_t<F> *partials, const uint32_t *o
     buckets[b] = acc;
 }
 
-// one warp per over-full bucket: lanes stride over its partials, then a shuffle tree
+// one BLOCK per over-full bucket: the 128 threads stride over its partials, a shuffle tree per warp, then the four
+// warp sums through shared memory.  (A window whose digits take only a few values — a short top window, or scalars
+// that are all equal — puts n / K partials into one bucket; 128 lanes keep that a few dozen serial additions.)
 template <class F>
 __global__ void BLS_LB k_msm_combine_big(const jac_t<F> *partials, const uint32_t *offsets, const uint32_t *rank, size_t b0,
                                          uint32_t K, const uint32_t *biglist, const uint32_t *bigcount, jac_t<F> *buckets) {
-    const int lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    __shared__ jac_t<F> wsum[4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t nbig = *bigcount;
-    for (size_t i = warp; i < nbig; i += nwarps) {
+    for (uint32_t i = blockIdx.x; i < nbig; i += gridDim.x) {
         const uint32_t b = biglist[b0 + i];
         uint32_t base, np;
         msm_bucket_slots(offsets, rank, b, K, offsets[b0], rank[b0], base, np);
         jac_t<F> acc;
         pt_set_inf(acc);
-        for (uint32_t t = lane; t < np; t += 32) {
+        for (uint32_t t = threadIdx.x; t < np; t += blockDim.x) {
             jac_t<F> x = partials[base + t];
             pt_add(acc, acc, x);
         }
@@ -263,7 +265,13 @@ __global__ void BLS_LB k_msm_combine_big(const jac_t<F> *partials, const uint32_
             for (int k = 0; k < (int)(sizeof(jac_t<F>) / 4); k++) dst[k] = __shfl_down_sync(0xffffffffu, src[k], o);
             pt_add(acc, acc, other);
         }
-        if (lane == 0) buckets[b] = acc;
+        if (lane == 0) wsum[wid] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 4; w++) { jac_t<F> x = wsum[w]; pt_add(acc, acc, x); }
+            buckets[b] = acc;
+        }
+        __syncthreads();
     }
 }
 
@@ -394,16 +402,26 @@ __global__ void BLS_LB k_msm_make_inputs(uint64_t seed, size_t n, g1_aff *points
     scalars[32 * i + 31] &= 0x7f;
 }
 
-// window width: ~log2(n) - 4, then the smallest width that needs the same number of windows
+// Window width c and count.  Cost model per candidate c: nwin * (11 n + 32 * 2^(c-1)) field multiplications (one
+// mixed addition per non-zero digit, two full additions per bucket in the reduction).  Signed digits put bit `nbits`
+// (the last carry) into the top window; a top window of only a few bits would funnel n / 2^bits entries into each of
+// its few buckets, so widths that leave it fewer than 6 bits are skipped (for nbits = 255: c = 16, 13, 10, 8 qualify).
 static inline void msm_shape(size_t n, int nbits, int &c, int &nwin) {
     int lg = 0;
     while ((n >> (lg + 1)) != 0) lg++;
-    c = lg - 4;
-    if (c < 2) c = 2;
-    if (c > 16) c = 16;
+    static const int c_env = getenv("BLSGPU_MSM_C") ? atoi(getenv("BLSGPU_MSM_C")) : 0;
+    int best_c = 0;
+    double best = 0.0;
+    const int hi = lg - 2 > 16 ? 16 : lg - 2, lo = lg - 8 < 2 ? 2 : lg - 8;
+    for (int cc = hi; cc >= lo; cc--) {
+        const int nw = (nbits + 1 + cc - 1) / cc, top = nbits + 1 - (nw - 1) * cc;
+        if (nw > 1 && top < (cc < 6 ? cc : 6)) continue;
+        const double cost = (double)nw * (11.0 * (double)n + 32.0 * (double)((size_t)1 << (cc - 1)));
+        if (!best_c || cost < best) { best_c = cc; best = cost; }
+    }
+    if (!best_c) best_c = lg - 4 < 2 ? 2 : (lg - 4 > 16 ? 16 : lg - 4);
+    c = c_env > 0 ? c_env : best_c;
     nwin = (nbits + 1 + c - 1) / c;
-    c = (nbits + 1 + nwin - 1) / nwin;
-    if (c < 2) c = 2;
 }
 
 // Stream-ordered: d_points (stride pstride bytes, aff_t<F> each) and d_scalars (stride sstride bytes, little-endian,
@@ -518,7 +536,7 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
             ts = st.tail;
         }
         k_msm_combine<F><<<(unsigned)(((size_t)wg * B + 127) / 128), 128, 0, ts>>>(pg, offsets, rank, b0, b1, K, buckets, biglist, bigcount + g);
-        k_msm_combine_big<F><<<64, 128, 0, ts>>>(pg, offsets, rank, b0, K, biglist, bigcount + g, buckets);
+        k_msm_combine_big<F><<<128, 128, 0, ts>>>(pg, offsets, rank, b0, K, biglist, bigcount + g, buckets);
         size_t nt = (size_t)wg * nseg;
         J *sg = segs + (size_t)w0 * nseg;
         k_msm_segment<F><<<(unsigned)((nt + 127) / 128), 128, 0, ts>>>(buckets + b0, c, wg, (uint32_t)L, sg);

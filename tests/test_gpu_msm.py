@@ -84,3 +84,34 @@ def test_msm_skewed_scalars(cache, br):
     g2 = _g2_points(br, 700)
     sc2 = (0xfedcba9876543210).to_bytes(8, "little") * 700
     assert bg.msmG2(cache, g2, sc2, 64) == br.msm_g2(g2, sc2, 64)
+
+
+def test_msm_g1_window_horner_edges(cache, br):
+    """The window Horner runs as a branch-free dataflow program over complete projective formulas (fpprog.hpp
+    build_msm_horner_g1): results at infinity, empty top windows, a lone low window and windows that cancel must come
+    out exactly as blst_p1s_mult_pippenger + to_affine gives them."""
+    import nim_blscurve_b200 as bg
+    n = 40
+    pts, sc = br.msm_points(31, n)
+    zero = bytes(32 * n)
+    assert bg.msmG1(cache, pts, zero, 255) == br.msm_g1(pts, zero, 255) == bytes(96)          # all windows infinite
+    small = b"".join((i + 1).to_bytes(32, "little") for i in range(n))                         # only window 0 is populated
+    assert bg.msmG1(cache, pts, small, 255) == br.msm_g1(pts, small, 255)
+    top = b"".join(((i + 1) << 240).to_bytes(32, "little") for i in range(n))                  # only the top bits
+    assert bg.msmG1(cache, pts, top, 255) == br.msm_g1(pts, top, 255)
+    # P_1 = -P_0 with equal scalars: every window sum cancels -> infinity; with different scalars: they do not
+    p = bytearray(pts[:192])
+    from oracle import pyref as pr
+    neg = pr.fp_to_mont_bytes((-pr.fp_from_mont_bytes(bytes(p[48:96]))) % pr.P)
+    p[96:144] = p[0:48]
+    p[144:192] = neg
+    s1 = sc[:32] * 2
+    assert bg.msmG1(cache, bytes(p), s1, 255) == br.msm_g1(bytes(p), s1, 255) == bytes(96)
+    s2 = sc[:64]
+    assert bg.msmG1(cache, bytes(p), s2, 255) == br.msm_g1(bytes(p), s2, 255)
+    # one point (c = 2, 128 windows): sparse and all-ones scalars; the P + P / P - P cases of the program's addition
+    # are pinned on the CPU in tests/test_hostsim.py::test_msm_horner_program
+    one = pts[:96]
+    for k in (1 << 16 | 1, (1 << 32) | (1 << 16) | 1, (1 << 255) - 1):
+        s = (k % (1 << 255)).to_bytes(32, "little")
+        assert bg.msmG1(cache, one, s, 255) == br.msm_g1(one, s, 255)
