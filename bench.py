@@ -373,6 +373,11 @@ def main():
                 t = br.time_batch_verify(sample, srb, cores, 1)
                 t1n = min(n, 4096)
                 t1 = br.time_batch_verify(sample[:t1n * 320], srb, 1, 1)
+                # the 129-set block batch on the host cores as well (best of 5: it is a latency comparison)
+                tblk = br.time_batch_verify(sample[:blk * 320], srb, cores, 5)
+                extra["block_batch"]["cpu_baseline"] = {
+                    "value": tblk * 1e3, "unit": "ms", "cores": cores, "kind": "reference",
+                    "sample": f"the same {blk} sets, BLST batchVerifyParallel replica, {cores} threads, best of 5"}
                 extra["cpu_baseline"] = {
                     "value": n / t, "unit": "sets/s", "cores": cores, "kind": "reference",
                     "sample": f"first {n} sets of the same workload, BLST (oracle/_ref) batchVerifyParallel replica, "
