@@ -93,3 +93,36 @@ def test_large_batch_properties(cache, br, srb):
         first, cnt = bg.shard_range(n, 4, r)
         parts += be.partial(bytes(bad)[first * 320:(first + cnt) * 320], first, n, srb, 64)[0]
     assert be.finalize(parts) == (ok, gt)
+
+
+def test_epoch_batch_full_size_properties(br, srb):
+    """The bench workload at full size (131 072 distinct-message sets, the per-GPU share of BASELINE configs[4]) through
+    size-independent properties: the valid batch verifies; one flipped message bit anywhere rejects it; the
+    post-final-exponentiation GT of the rejected batch does not depend on how the batch is cut into rank shares
+    (8 shares cut by the reference chunk rule vs one context); and a 1 500-set window around the corrupted
+    set is pinned against BLST."""
+    import nim_blscurve_b200 as bg
+    n = 131072
+    big = bg.BatchedBLSVerifierCache(max_sets=n, device=0)
+    try:
+        out = (C.c_uint8 * (320 * n))()
+        assert bg.lib().blsgpu_make_sets(big.handle, 2026, 0, n, out, 0) == 0
+        sets = bytes(out)
+        assert big.verify_raw(sets, srb, 1024) is True
+        victim = 100003
+        bad = bytearray(sets)
+        bad[victim * 320 + 96 + 31] ^= 0x01
+        bad = bytes(bad)
+        ok, gt = big.verify_raw(bad, srb, 1024, want_gt=True)
+        assert ok is False
+        be = bg.GpuBackend(big)
+        parts = b""
+        for r in range(8):
+            first, cnt = bg.shard_range(n, 8, r)
+            parts += be.partial(bad[first * 320:(first + cnt) * 320], first, n, srb, 1024)[0]
+        assert be.finalize(parts) == (ok, gt)
+        w0 = victim - 700
+        window = bad[w0 * 320:(w0 + 1500) * 320]
+        assert big.verify_raw(window, srb, 16, want_gt=True) == br.batch_verify(window, srb, 16)
+    finally:
+        big.close()

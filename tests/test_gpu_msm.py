@@ -115,3 +115,49 @@ def test_msm_g1_window_horner_edges(cache, br):
     for k in (1 << 16 | 1, (1 << 32) | (1 << 16) | 1, (1 << 255) - 1):
         s = (k % (1 << 255)).to_bytes(32, "little")
         assert bg.msmG1(cache, one, s, 255) == br.msm_g1(one, s, 255)
+
+
+def _device_msm_inputs(cache, n, seed):
+    import torch
+    import nim_blscurve_b200 as bg
+    dp = torch.empty(n * 96, dtype=torch.uint8, device="cuda")
+    ds = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    assert bg.lib().blsgpu_msm_make_inputs(cache.handle, seed, n, C.c_void_p(dp.data_ptr()), C.c_void_p(ds.data_ptr())) == 0
+    return dp, ds
+
+
+def _msm_dev(cache, dp, ds, n, first=0, nbits=255):
+    import nim_blscurve_b200 as bg
+    out = (C.c_uint8 * 96)()
+    rc = bg.lib().blsgpu_msm_g1_dev(cache.handle, C.c_void_p(dp.data_ptr() + 96 * first),
+                                    C.c_void_p(ds.data_ptr() + 32 * first), n, nbits, out)
+    assert rc == 1, cache.last_error()
+    return bytes(out)
+
+
+def test_msm_g1_full_size_vs_blst(cache, br):
+    """BASELINE configs[2] at its headline size: 2^20 points, 255-bit scalars, against blst_p1s_mult_pippenger
+    (one host thread, ~8 s) on the same bytes."""
+    n = 1 << 20
+    dp, ds = _device_msm_inputs(cache, n, 0xFACADE)
+    got = _msm_dev(cache, dp, ds, n)
+    assert got == br.msm_g1(dp.cpu().numpy().tobytes(), ds.cpu().numpy().tobytes(), 255)
+
+
+def test_msm_g1_size_independent_properties(cache, br):
+    """2^21 points (beyond what the oracle finishes quickly): the sum over the whole range equals the aggregate
+    (aggregateAll, a different code path) of the sums over four unequal slices — slices of 2^19, 2^20 and two odd
+    sizes use different window shapes (c = 16, 16, 13...), so this also checks shape independence; and a slice that
+    fits the oracle budget is pinned against BLST."""
+    import nim_blscurve_b200 as bg
+    n = 1 << 21
+    dp, ds = _device_msm_inputs(cache, n, 77)
+    whole = _msm_dev(cache, dp, ds, n)
+    cuts = [0, 1 << 19, (1 << 19) + (1 << 20), (1 << 21) - 70001, n]
+    parts = [_msm_dev(cache, dp, ds, cuts[i + 1] - cuts[i], cuts[i]) for i in range(4)]
+    ok, total = bg.aggregateAll(cache, parts)
+    assert ok and total == whole
+    lo, cnt = cuts[3], cuts[4] - cuts[3]
+    pts = dp[96 * lo:96 * (lo + cnt)].cpu().numpy().tobytes()
+    sc = ds[32 * lo:32 * (lo + cnt)].cpu().numpy().tobytes()
+    assert parts[3] == br.msm_g1(pts, sc, 255)
