@@ -49,8 +49,8 @@ struct blsgpu_ctx {
     size_t misc_bytes = 0;
     void *d_misc2 = nullptr;      // small result scratch (MSM output)
     uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
-    cudaEvent_t ev[2 * ST_COUNT + 2];                        // stage begin/end pairs + fork/join
-    bool ev_valid[2 * ST_COUNT + 2];
+    cudaEvent_t ev[2 * ST_COUNT + 3];                        // stage begin/end pairs + fork/join/G1-ready
+    bool ev_valid[2 * ST_COUNT + 3];
     cudaStream_t side = nullptr;                             // the signature-side MSM runs beside the per-set stages
     bool use_side = true;
     float stage_ms[ST_COUNT];
@@ -105,7 +105,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     cudaFree(ctx->d_norm); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (int i = 0; i < 2 * ST_COUNT + 2; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2 * ST_COUNT + 3; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -119,7 +119,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     blsgpu_ctx *ctx = new blsgpu_ctx();
     ctx->device = device;
     ctx->cap = max_sets;
-    for (int i = 0; i < 2 * ST_COUNT + 2; i++) ctx->ev_valid[i] = false;
+    for (int i = 0; i < 2 * ST_COUNT + 3; i++) ctx->ev_valid[i] = false;
     for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
     cudaError_t e = cudaSetDevice(device);
     auto bad = [&](const char *what, cudaError_t err) {
@@ -163,7 +163,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bad("cudaDeviceSynchronize", e);
     ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
     if (getenv("BLSGPU_ACC_TEAM")) ctx->acc_team = atoi(getenv("BLSGPU_ACC_TEAM")) != 0;
-    for (int i = 0; i < 2 * ST_COUNT + 2; i++) {
+    for (int i = 0; i < 2 * ST_COUNT + 3; i++) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
         ctx->ev_valid[i] = true;
     }
@@ -205,6 +205,7 @@ static words8 words_of(const uint8_t b[32]) {
 #define END(stage, st) CK(cudaEventRecord(ctx->ev[2 * (stage) + 1], st))
 #define EV_FORK (2 * ST_COUNT)
 #define EV_JOIN (2 * ST_COUNT + 1)
+#define EV_G1 (2 * ST_COUNT + 2)
 
 // scalars for global indices [first, first+n) into d_r
 static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size_t first, size_t total_n,
@@ -264,7 +265,22 @@ static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp 
 // Work decomposition of the accumulation: G pairs per group (they share the Fp12 squarings) and nseg loop segments,
 // chosen so that groups x segments gives every SM several warps even for small batches.
 static void miller_shape(size_t np, bool team, int &G, int &nseg) {
-    if (team) {                                    // ~32k teams: 6 lanes each, squarings are cheap to share widely
+    if (team && np <= 8192) {
+        // Latency regime (the machine is not full).  Measured on B200 (tools/gpu_small_sweep.sh): a team spends ~7.5 us
+        // per (squaring or line) step while all teams are resident (~12k of them), the product over groups is one
+        // block-wide tree (0.59 ms) up to 128 groups and two launches (1.16 ms) beyond, the segment Horner program costs
+        // 0.22 ms + 7.4 us per segment.
+        double best = 0.0;
+        G = 1; nseg = 32;
+        for (int g = 1; g <= 64; g *= 2)
+            for (int ns = 4; ns <= 32; ns *= 2) {
+                const size_t ngroups = (np + g - 1) / g;
+                const double waves = (double)((ngroups * ns + 11999) / 12000);
+                const double acc = waves * (double)((63 + ns - 1) / ns) * (1 + g) * 7.5e-3;
+                const double cost = acc + (ngroups <= 128 ? 0.59 : 1.16) + 0.22 + 7.4e-3 * ns;
+                if (best == 0.0 || cost < best) { best = cost; G = g; nseg = ns; }
+            }
+    } else if (team) {                             // ~32k teams: 6 lanes each, squarings are cheap to share widely
         G = 1;
         while (G < 16 && np / (size_t)(2 * G) >= 4096) G *= 2;
         size_t ngroups = (np + G - 1) / G;
@@ -367,6 +383,15 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         CK(cudaEventRecord(ctx->ev[EV_FORK], s));
         CK(cudaStreamWaitEvent(g, ctx->ev[EV_FORK], 0));
     }
+    // Small batches are latency chains (one thread per set): [r_i]pk_i does not depend on H(m_i), so it leads the
+    // second stream instead of queueing behind the hash kernel.  Large batches fill the machine either way.
+    const bool g1_aside = ctx->use_side && n < 2048;
+    if (g1_aside) {
+        BEGIN(ST_G1MUL, g);
+        k_g1_mul<<<nblk(n), 128, 0, g>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
+        END(ST_G1MUL, g);
+        CK(cudaEventRecord(ctx->ev[EV_G1], g));
+    }
     BEGIN(ST_G2MUL, g);
     // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
     // buckets, n independent 64-bit multiplications + tree below that
@@ -395,13 +420,20 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     END(ST_G2SUM, g);
     if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_JOIN], g));
     BEGIN(ST_HASH, s);
-    k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+    if (n <= 8192) k_hash_sets_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+    else k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
     END(ST_HASH, s);
-    BEGIN(ST_G1MUL, s);
-    k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
-    END(ST_G1MUL, s);
+    if (g1_aside) {
+        CK(cudaStreamWaitEvent(s, ctx->ev[EV_G1], 0));
+    } else {
+        BEGIN(ST_G1MUL, s);
+        k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
+        END(ST_G1MUL, s);
+    }
     BEGIN(ST_AFFINE, s);
-    k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P);
+    // a handful of sets: one inversion on one or two threads is pure latency -> binary Euclid (it diverges across the
+    // lanes of a warp, so from a few dozen sets on the uniform Fermat chain is as quick: measured 0.53 vs 0.46 ms at 129)
+    k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, n <= 16 ? 1 : 0);
     END(ST_AFFINE, s);
     ctx->launches += 3;
     if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));   // join: pair number n is in place

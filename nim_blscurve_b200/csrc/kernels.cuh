@@ -130,6 +130,34 @@ __global__ void BLS_LB k_hash_sets(const sigset *sets, size_t n, g2_jac *H) {
     H[i] = h;
 }
 
+// Small batches: two lanes per message, one SSWU map each (the two maps of hash_to_curve are independent and are a
+// fifth of the serial work); the odd lane hands its point to the even lane, which adds, applies the isogeny and clears
+// the cofactor.  Same result as k_hash_sets; used while 2n threads still leave the machine under-filled.
+__global__ void BLS_LB k_hash_sets_pair(const sigset *sets, size_t n, g2_jac *H) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = t >> 1;
+    const bool odd = t & 1;
+    const bool live = i < n;
+    uint8_t msg[32], dst[43];
+    for (int k = 0; k < 32; k++) msg[k] = live ? sets[i].msg[k] : 0;
+    for (int k = 0; k < 43; k++) dst[k] = DST_ETH2[k];
+    fp2 u0, u1;
+    hash_to_field_fp2x2(u0, u1, msg, 32, dst, 43);
+    g2_jac q, other;
+    sswu_g2(q, odd ? u1 : u0);
+    {
+        uint32_t *d = (uint32_t *)&other;
+        const uint32_t *sp = (const uint32_t *)&q;
+        for (int k = 0; k < (int)(sizeof(g2_jac) / 4); k++) d[k] = __shfl_down_sync(0xffffffffu, sp[k], 1);
+    }
+    if (odd || !live) return;
+    pt_add(q, q, other, &SSWU_A);
+    iso3_g2(q, q);
+    g2_jac h;
+    g2_clear_cofactor(h, q);
+    H[i] = h;
+}
+
 __global__ void BLS_LB k_g1_mul(const sigset *sets, const uint64_t *r, size_t n, g1_jac *Pj, int *flags) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -144,7 +172,7 @@ __global__ void BLS_LB k_g1_mul(const sigset *sets, const uint64_t *r, size_t n,
 // one inverse, and every thread walks AFF_B sets (strided by the thread count, so that warps stay coalesced) and
 // shares ONE Fermat inversion among them: 1 inversion + ~45 multiplications per set become 1/8 inversion + ~50.
 #define AFF_B 8
-__global__ void BLS_LB k_pairs_affine(const g2_jac *H, const g1_jac *Pj, size_t n, g2_aff *Q, g1_aff *P) {
+__global__ void BLS_LB k_pairs_affine(const g2_jac *H, const g1_jac *Pj, size_t n, g2_aff *Q, g1_aff *P, int vartime) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
     if (t >= n) return;
     fp nz[AFF_B], zp[AFF_B], pre[AFF_B];
@@ -168,7 +196,7 @@ __global__ void BLS_LB k_pairs_affine(const g2_jac *H, const g1_jac *Pj, size_t 
         cnt = k + 1;
     }
     fp inv;
-    fp_inv(inv, pre[cnt - 1]);
+    if (vartime) fp_inv_vartime(inv, pre[cnt - 1]); else fp_inv(inv, pre[cnt - 1]);
     for (int k = cnt - 1; k >= 0; k--) {
         const size_t i = t + (size_t)k * nthreads;
         fp ik, ninv, zpinv, tt;
