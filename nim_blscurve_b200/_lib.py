@@ -53,6 +53,7 @@ def lib():
     L.blsgpu_partial_dev.argtypes = [vp, vp, sz, sz, sz, u8p, C.c_uint32, vp, vp]
     L.blsgpu_finalize_dev.argtypes = [vp, vp, sz, vp, vp]
     L.blsgpu_hash_to_g2.argtypes = [vp, vp, sz, sz, vp, sz, vp, vp]
+    L.blsgpu_test_small_hash.argtypes = [vp, vp, sz, vp, vp]
     L.blsgpu_aggregate_g1.argtypes = [vp, vp, sz, vp]
     L.blsgpu_aggregate_g2.argtypes = [vp, vp, sz, vp]
     L.blsgpu_msm_g1.argtypes = [vp, vp, vp, sz, sz, vp]

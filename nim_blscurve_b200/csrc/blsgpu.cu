@@ -58,7 +58,8 @@ struct blsgpu_ctx {
     msm_state msm;
     // warp-cooperative tail programs (fpprog.hpp), compiled on first use and kept on the device
     struct dev_prog { uint32_t *d = nullptr; int nslots = 0, nrounds = 0; };
-    std::map<int, dev_prog> combine_progs, final_progs, norm_progs;   // keyed by segment count / partial count
+    std::map<int, dev_prog> combine_progs, final_progs, norm_progs, set_progs;   // keyed by segment count / partial count
+    fp *d_small = nullptr;                                   // per-set program inputs/outputs of the small-batch route
     fp *d_norm = nullptr;                                    // [0] Fp norm taken out of the final exponentiation, [1] its inverse
     fp *d_consts = nullptr;                                  // Frobenius coefficients (fpprog::CONST_*)
     fp12 *d_gt = nullptr;                                    // final exponentiation result, Montgomery form
@@ -102,7 +103,8 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     for (auto &kv : ctx->combine_progs) cudaFree(kv.second.d);
     for (auto &kv : ctx->final_progs) cudaFree(kv.second.d);
     for (auto &kv : ctx->norm_progs) cudaFree(kv.second.d);
-    cudaFree(ctx->d_norm); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
+    for (auto &kv : ctx->set_progs) cudaFree(kv.second.d);
+    cudaFree(ctx->d_norm); cudaFree(ctx->d_small); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2 * ST_COUNT + 3; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
@@ -160,6 +162,11 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
         (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB2, FROB2, sizeof(FROB2), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
         (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB3, FROB3, sizeof(FROB3), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess)
         return bad("cudaMemcpyFromSymbol(FROB)", e);
+    if ((e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_PSI_CX, PSI_CX, sizeof(PSI_CX), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
+        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_PSI_CY, PSI_CY, sizeof(PSI_CY), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
+        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_PSI2_CX, PSI2_CX, sizeof(PSI2_CX), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
+        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_ONE, FP_ONE, sizeof(FP_ONE), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess)
+        return bad("cudaMemcpyFromSymbol(PSI)", e);
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bad("cudaDeviceSynchronize", e);
     ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
     if (getenv("BLSGPU_ACC_TEAM")) ctx->acc_team = atoi(getenv("BLSGPU_ACC_TEAM")) != 0;
@@ -224,10 +231,13 @@ static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size
     return 0;
 }
 
+enum { SETPROG_COFACTOR = 0, SETPROG_G2MUL64 = 1 };
+
 // Compile (once) and fetch a tail program; kind 0 = combine over `key` segments, 1 = final exponentiation of `key`
-// partials with the Fp inversion supplied in IN1, 2 = the norm that inversion applies to (fpprog.hpp build_final)
+// partials with the Fp inversion supplied in IN1, 2 = the norm that inversion applies to (fpprog.hpp build_final),
+// 3 = per-set G2 program `key` (SETPROG_*)
 static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &out) {
-    std::map<int, blsgpu_ctx::dev_prog> &cache = kind == 0 ? ctx->combine_progs : (kind == 1 ? ctx->final_progs : ctx->norm_progs);
+    std::map<int, blsgpu_ctx::dev_prog> &cache = kind == 0 ? ctx->combine_progs : (kind == 1 ? ctx->final_progs : (kind == 2 ? ctx->norm_progs : ctx->set_progs));
     auto it = cache.find(key);
     if (it != cache.end()) { out = it->second; return 0; }
     fpprog::Program P;
@@ -235,6 +245,8 @@ static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &ou
         int len[64];
         for (int j = 0; j < key; j++) len[j] = ml_seg_hi(j, key) - ml_seg_lo(j, key) + 1;
         P = fpprog::build_combine(key, len);
+    } else if (kind == 3) {                              // per-set programs of the small-batch route
+        P = key == SETPROG_COFACTOR ? fpprog::build_g2_clear_cofactor() : fpprog::build_g2_mul64();
     } else {
         P = fpprog::build_final(key, kind == 1 ? fpprog::INV_EXTERNAL : fpprog::INV_EMIT_ARG);
     }
@@ -257,10 +269,21 @@ static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp 
         static bool raised = false;
         if (!raised) { CK(cudaFuncSetAttribute(k_fp_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); raised = true; }
     }
-    k_fp_program<<<1, 32, smem, ctx->stream>>>(p.d, in0, in1, ctx->d_consts, out0);
+    k_fp_program<<<1, 32, smem, ctx->stream>>>(p.d, in0, in1, ctx->d_consts, out0, 0, 0, 0);
     ctx->launches++;
     return 0;
 }
+
+// one warp per instance: n instances of a per-set program on stream st, strides in field elements
+static int launch_prog_many(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, cudaStream_t st, size_t n, const fp *in0, size_t s_in0,
+                            const fp *in1, size_t s_in1, fp *out0, size_t s_out) {
+    k_fp_program<<<(unsigned)n, 32, (size_t)p.nslots * sizeof(fp), st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
+    ctx->launches++;
+    return 0;
+}
+
+#define SMALL_ROUTE_MAX 1024            // sets; beyond this a warp per set no longer fits the machine in one wave
+#define SMALL_FP_PER_SET (6 + 6 + 6 + 6 + 64)
 
 // Work decomposition of the accumulation: G pairs per group (they share the Fp12 squarings) and nseg loop segments,
 // chosen so that groups x segments gives every SM several warps even for small batches.
@@ -392,6 +415,24 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         END(ST_G1MUL, g);
         CK(cudaEventRecord(ctx->ev[EV_G1], g));
     }
+    // Small-batch route: the serial stretches of a set (cofactor clearing, [r_i] sig_i) run as per-set dataflow
+    // programs, one warp per set (fpprog.hpp build_g2_clear_cofactor / build_g2_mul64)
+    static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 3;   // bit 0 hash, bit 1 sig
+    const bool small = small_env != 0 && n <= SMALL_ROUTE_MAX && !ctx->serial_tail;
+    const bool small_hash = small && (small_env & 1), small_sig = small && (small_env & 2);
+    blsgpu_ctx::dev_prog p_cof, p_mul;
+    fp *sm_hash_in = nullptr, *sm_hash_out = nullptr, *sm_sig_in = nullptr, *sm_sig_out = nullptr, *sm_bits = nullptr;
+    if (small) {
+        if (!ctx->d_small) CK(cudaMalloc((void **)&ctx->d_small, (size_t)SMALL_ROUTE_MAX * SMALL_FP_PER_SET * sizeof(fp)));
+        rc = get_prog(ctx, 3, SETPROG_COFACTOR, p_cof);
+        if (!rc) rc = get_prog(ctx, 3, SETPROG_G2MUL64, p_mul);
+        if (rc) return rc;
+        sm_hash_in = ctx->d_small;
+        sm_hash_out = sm_hash_in + 6 * SMALL_ROUTE_MAX;
+        sm_sig_in = sm_hash_out + 6 * SMALL_ROUTE_MAX;
+        sm_sig_out = sm_sig_in + 6 * SMALL_ROUTE_MAX;
+        sm_bits = sm_sig_out + 6 * SMALL_ROUTE_MAX;
+    }
     BEGIN(ST_G2MUL, g);
     // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
     // buckets, n independent 64-bit multiplications + tree below that
@@ -404,8 +445,15 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         END(ST_G2MUL, g);
         BEGIN(ST_G2SUM, g);
     } else {
-        k_g2_mul<<<nblk(n), 128, 0, g>>>(d_sets, ctx->d_r, n, ctx->d_S);
-        ctx->launches++;
+        if (small_sig) {
+            k_g2_mul_prep<<<nblk(64 * n), 128, 0, g>>>(d_sets, ctx->d_r, n, sm_sig_in, sm_bits);
+            launch_prog_many(ctx, p_mul, g, n, sm_sig_in, 6, sm_bits, 64, sm_sig_out, 6);
+            k_g2_hom_to_jac<<<nblk(n), 128, 0, g>>>(sm_sig_out, n, ctx->d_S);
+            ctx->launches += 2;
+        } else {
+            k_g2_mul<<<nblk(n), 128, 0, g>>>(d_sets, ctx->d_r, n, ctx->d_S);
+            ctx->launches++;
+        }
         END(ST_G2MUL, g);
         BEGIN(ST_G2SUM, g);
         for (size_t m = n; m > 1;) {
@@ -420,7 +468,12 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     END(ST_G2SUM, g);
     if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_JOIN], g));
     BEGIN(ST_HASH, s);
-    if (n <= 8192) k_hash_sets_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+    if (small_hash) {
+        k_hash_map_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, sm_hash_in);
+        launch_prog_many(ctx, p_cof, s, n, sm_hash_in, 6, nullptr, 0, sm_hash_out, 6);
+        k_g2_hom_to_jac<<<nblk(n), 128, 0, s>>>(sm_hash_out, n, ctx->d_H);
+        ctx->launches += 2;
+    } else if (n <= 8192) k_hash_sets_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
     else k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
     END(ST_HASH, s);
     if (g1_aside) {
@@ -628,6 +681,27 @@ extern "C" int blsgpu_hash_to_g2(blsgpu_ctx *ctx, const uint8_t *msgs, size_t n,
     CK(cudaGetLastError());
     if (out_affine) CK(cudaMemcpyAsync(out_affine, base + o_aff, n * 192, cudaMemcpyDeviceToHost, s));
     if (out_compressed) CK(cudaMemcpyAsync(out_compressed, base + o_comp, n * 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Test hook: the hash of the small-batch route up to (and including) the cofactor-clearing program.
+// out_in / out_out: n x 6 field elements each (homogeneous point before / after the program), host buffers.
+extern "C" int blsgpu_test_small_hash(blsgpu_ctx *ctx, const void *sets320, size_t n, uint8_t *out_in, uint8_t *out_out) {
+    if (!ctx || !sets320 || n == 0 || n > SMALL_ROUTE_MAX || n > ctx->cap) return BLSGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (!ctx->d_small) CK(cudaMalloc((void **)&ctx->d_small, (size_t)SMALL_ROUTE_MAX * SMALL_FP_PER_SET * sizeof(fp)));
+    blsgpu_ctx::dev_prog p_cof;
+    int rc = get_prog(ctx, 3, SETPROG_COFACTOR, p_cof);
+    if (rc) return rc;
+    fp *hin = ctx->d_small, *hout = hin + 6 * SMALL_ROUTE_MAX;
+    CK(cudaMemcpyAsync(ctx->d_sets, sets320, n * 320, cudaMemcpyHostToDevice, s));
+    k_hash_map_pair<<<nblk(2 * n), 128, 0, s>>>(ctx->d_sets, n, hin);
+    launch_prog_many(ctx, p_cof, s, n, hin, 6, nullptr, 0, hout, 6);
+    CK(cudaGetLastError());
+    if (out_in) CK(cudaMemcpyAsync(out_in, hin, n * 6 * sizeof(fp), cudaMemcpyDeviceToHost, s));
+    if (out_out) CK(cudaMemcpyAsync(out_out, hout, n * 6 * sizeof(fp), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return 0;
 }

@@ -25,7 +25,8 @@ enum { LANES = 32, MAX_SLOTS = 1024, ROUND_WORDS = LANES };
 // buffer ids of the I/O tables
 enum { BUF_IN0 = 0, BUF_IN1 = 1, BUF_CONST = 2, BUF_OUT0 = 3 };
 // fp indices inside the constant pool (BUF_CONST): Frobenius coefficients as fp2 = 2 fp each
-enum { CONST_FROB1 = 0, CONST_FROB2 = 10, CONST_FROB3 = 20, CONST_COUNT = 30 };
+enum { CONST_FROB1 = 0, CONST_FROB2 = 10, CONST_FROB3 = 20, CONST_PSI_CX = 30, CONST_PSI_CY = 32, CONST_PSI2_CX = 34, CONST_ONE = 35,
+       CONST_COUNT = 36 };
 
 struct Node { uint8_t op; int32_t a, b; };
 struct IoRef { int32_t node, buf, idx; };
@@ -369,35 +370,45 @@ inline Program build_final(int count, int inv_mode = INV_INLINE) {
 // P - P and P + infinity all come out of the same straight line — which is what a branch-free dataflow program needs.
 // The point carries N = 2Z and M = 6Z so that the doubling needs no constant multiplications and only shallow
 // addition chains between its two multiplication levels (12 Z^2 = M N, 36 Z^2 = M^2, 8 Y^2 Y Z = 4 Y^2 (Y N)).
-struct VP { V x, y, z, n, m; };
-inline VP vp_make(V x, V y, V z) {
-    V n = z + z, n2 = n + n;
-    return {x, y, z, n, n2 + n};
-}
-inline VP rcb_dbl(VP p) {
-    V A = p.y * p.y, B2 = p.y * p.n, D = p.x * p.y, E36 = p.m * p.m, E12 = p.m * p.n;
-    V t0 = A - E36, ys = A + E12;
-    V A2 = A + A, A4 = A2 + A2, A8 = A4 + A4;
-    V xh = D * t0, yp = t0 * ys, yq = A8 * E12, z3 = A4 * B2, n3 = A8 * B2;
-    V n6 = n3 + n3;
-    return {xh + xh, yp + yq, z3, n3, n6 + n3};
-}
-inline V mul12(V a) {
-    V a2 = a + a, a4 = a2 + a2, a8 = a4 + a4;
+// Written over the field type: V for G1 (b3 = 12), V2 for G2 on the twist y^2 = x^3 + 4(1+u) (b3 = 12(1+u)).
+template <class T> struct PT { T x, y, z, n, m; };
+typedef PT<V> VP;
+inline V t_sqr(V a) { return a * a; }
+inline V2 t_sqr(V2 a) { return sqr(a); }
+template <class T> inline T mul12(T a) {
+    T a2 = a + a, a4 = a2 + a2, a8 = a4 + a4;
     return a8 + a4;
 }
-inline VP rcb_add(VP p, VP q) {
-    V t0 = p.x * q.x, t1 = p.y * q.y, t2 = p.z * q.z;
-    V t3 = (p.x + p.y) * (q.x + q.y) - (t0 + t1);
-    V t4 = (p.y + p.z) * (q.y + q.z) - (t1 + t2);
-    V y3 = (p.x + p.z) * (q.x + q.z) - (t0 + t2);
-    V t0x3 = t0 + t0 + t0;
-    V t2b = mul12(t2);
-    V z3 = t1 + t2b, t1m = t1 - t2b;
-    V y3b = mul12(y3);
-    V x3 = t3 * t1m - t4 * y3b;
-    V yy = y3b * t0x3 + t1m * z3;
-    V zz = z3 * t4 + t0x3 * t3;
+inline V t_xi(V a) { return a; }                 // the (1+u) factor of the G2 curve constant; 1 on G1
+inline V2 t_xi(V2 a) { return mul_xi(a); }
+inline V t_neg(V a) { return vneg(a); }
+inline V2 t_neg(V2 a) { return neg(a); }
+template <class T> inline PT<T> vp_make(T x, T y, T z) {
+    T n = z + z, n2 = n + n;
+    return {x, y, z, n, n2 + n};
+}
+template <class T> inline PT<T> rcb_neg(PT<T> p) { return {p.x, t_neg(p.y), p.z, p.n, p.m}; }
+template <class T> inline PT<T> rcb_dbl(PT<T> p) {
+    // b3 Z^2 = xi * M N, 3 b3 Z^2 = xi * M^2
+    T A = t_sqr(p.y), B2 = p.y * p.n, D = p.x * p.y, E36 = t_xi(t_sqr(p.m)), E12 = t_xi(p.m * p.n);
+    T t0 = A - E36, ys = A + E12;
+    T A2 = A + A, A4 = A2 + A2, A8 = A4 + A4;
+    T xh = D * t0, yp = t0 * ys, yq = A8 * E12, z3 = A4 * B2, n3 = A8 * B2;
+    T n6 = n3 + n3;
+    return {xh + xh, yp + yq, z3, n3, n6 + n3};
+}
+template <class T> inline PT<T> rcb_add(PT<T> p, PT<T> q) {
+    T t0 = p.x * q.x, t1 = p.y * q.y, t2 = p.z * q.z;
+    T t3 = (p.x + p.y) * (q.x + q.y) - (t0 + t1);
+    T t4 = (p.y + p.z) * (q.y + q.z) - (t1 + t2);
+    T y3 = (p.x + p.z) * (q.x + q.z) - (t0 + t2);
+    T t0x3 = t0 + t0 + t0;
+    T t2b = t_xi(mul12(t2));
+    T z3 = t1 + t2b, t1m = t1 - t2b;
+    T y3b = t_xi(mul12(y3));
+    T x3 = t3 * t1m - t4 * y3b;
+    T yy = y3b * t0x3 + t1m * z3;
+    T zz = z3 * t4 + t0x3 * t3;
     return vp_make(x3, yy, zz);
 }
 
@@ -407,7 +418,7 @@ inline VP rcb_add(VP p, VP q) {
 inline Program build_msm_horner_g1(int nwin, int c) {
     Builder b;
     g_b = &b;
-    auto load = [&](int w) { return vp_make({b.leaf(BUF_IN0, 3 * w)}, {b.leaf(BUF_IN0, 3 * w + 1)}, {b.leaf(BUF_IN0, 3 * w + 2)}); };
+    auto load = [&](int w) { return vp_make<V>({b.leaf(BUF_IN0, 3 * w)}, {b.leaf(BUF_IN0, 3 * w + 1)}, {b.leaf(BUF_IN0, 3 * w + 2)}); };
     VP acc = load(nwin - 1);
     for (int w = nwin - 2; w >= 0; w--) {
         for (int k = 0; k < c; k++) acc = rcb_dbl(acc);
@@ -416,6 +427,67 @@ inline Program build_msm_horner_g1(int nwin, int c) {
     b.output(acc.x.id, BUF_OUT0, 0);
     b.output(acc.y.id, BUF_OUT0, 1);
     b.output(acc.z.id, BUF_OUT0, 2);
+    g_b = nullptr;
+    return compile(b);
+}
+
+// ---- per-set G2 programs of the small-batch route (one warp per signature set, k_fp_program_many) ----------------
+inline PT<V2> load_g2(int buf, int base) {
+    V2 x = {{g_b->leaf(buf, base)}, {g_b->leaf(buf, base + 1)}}, y = {{g_b->leaf(buf, base + 2)}, {g_b->leaf(buf, base + 3)}};
+    V2 z = {{g_b->leaf(buf, base + 4)}, {g_b->leaf(buf, base + 5)}};
+    return vp_make(x, y, z);
+}
+inline void store_g2(PT<V2> p, int buf, int base) {
+    V2 c[3] = {p.x, p.y, p.z};
+    for (int k = 0; k < 3; k++) { g_b->output(c[k].c0.id, buf, base + 2 * k); g_b->output(c[k].c1.id, buf, base + 2 * k + 1); }
+}
+inline V2 cfp2(int idx) { return {{g_b->leaf(BUF_CONST, idx)}, {g_b->leaf(BUF_CONST, idx + 1)}}; }
+// psi(X : Y : Z) = (conj(X) cx : conj(Y) cy : conj(Z)) (e2.c:455-482 on homogeneous coordinates), psi^2 likewise
+inline PT<V2> g2_psi(PT<V2> p) { return vp_make(conj(p.x) * cfp2(CONST_PSI_CX), conj(p.y) * cfp2(CONST_PSI_CY), conj(p.z)); }
+inline PT<V2> g2_psi2(PT<V2> p) { return {mul_fp(p.x, {g_b->leaf(BUF_CONST, CONST_PSI2_CX)}), neg(p.y), p.z, p.n, p.m}; }
+// [x]P, x = -0xd201000000010000
+inline PT<V2> g2_mul_by_x(PT<V2> p) {
+    PT<V2> acc = p;
+    for (int i = 62; i >= 0; i--) {
+        acc = rcb_dbl(acc);
+        if ((Z_ABS >> i) & 1) acc = rcb_add(acc, p);
+    }
+    return rcb_neg(acc);
+}
+// clear_cofactor (map_to_g2.c:327-349), same combination as g2_clear_cofactor in h2c.cuh.
+// IN0[0..5] = (X : Y : Z) homogeneous on E2, OUT0[0..5] = [h_eff] of it.
+inline Program build_g2_clear_cofactor() {
+    Builder b;
+    g_b = &b;
+    PT<V2> p = load_g2(BUF_IN0, 0);
+    PT<V2> t1 = g2_mul_by_x(p);
+    PT<V2> t2 = g2_psi(p);
+    PT<V2> t3 = g2_psi2(rcb_dbl(p));
+    t3 = rcb_add(t3, rcb_neg(t2));
+    t2 = g2_mul_by_x(rcb_add(t1, t2));
+    t3 = rcb_add(t3, t2);
+    t3 = rcb_add(t3, rcb_neg(t1));
+    store_g2(rcb_add(t3, rcb_neg(p)), BUF_OUT0, 0);
+    g_b = nullptr;
+    return compile(b);
+}
+// [k]Q for a 64-bit k given as 64 field elements 0 / 1 (IN1[0..63], least significant first; Montgomery form), Q
+// homogeneous in IN0[0..5]: double-and-always-add with the addend (b X : b Y + (1 - b) : b Z), which is Q for b = 1 and
+// the point at infinity (0 : 1 : 0) for b = 0 — complete formulas make the zero bits cost nothing but their lanes.
+inline Program build_g2_mul64() {
+    Builder b;
+    g_b = &b;
+    PT<V2> q = load_g2(BUF_IN0, 0);
+    V one = {b.leaf(BUF_CONST, CONST_ONE)};
+    auto addend = [&](int bit) {
+        V bb = {b.leaf(BUF_IN1, bit)};
+        V2 y = mul_fp(q.y, bb);
+        y.c0 = y.c0 + (one - bb);
+        return vp_make(mul_fp(q.x, bb), y, mul_fp(q.z, bb));
+    };
+    PT<V2> acc = addend(63);
+    for (int i = 62; i >= 0; i--) acc = rcb_add(rcb_dbl(acc), addend(i));
+    store_g2(acc, BUF_OUT0, 0);
     g_b = nullptr;
     return compile(b);
 }

@@ -158,6 +158,75 @@ __global__ void BLS_LB k_hash_sets_pair(const sigset *sets, size_t n, g2_jac *H)
     H[i] = h;
 }
 
+// ---- small-batch route (<= 1024 sets): the long serial stretches run as per-set dataflow programs ----
+// homogeneous (X : Y : Z) over Fp2 <- Jacobian; infinity -> (0 : 1 : 0)
+BLS_NOINLINE void g2_jac_to_hom(fp *hom, const g2_jac &p) {
+    fp2 x, y, z;
+    if (pt_is_inf(p)) {
+        fp2_set_zero(x); fp2_set_zero(y); y.c0 = FP_ONE; fp2_set_zero(z);
+    } else {
+        fp2 z2;
+        fp2_mul(x, p.x, p.z);
+        y = p.y;
+        fp2_sqr(z2, p.z);
+        fp2_mul(z, z2, p.z);
+    }
+    hom[0] = x.c0; hom[1] = x.c1; hom[2] = y.c0; hom[3] = y.c1; hom[4] = z.c0; hom[5] = z.c1;
+}
+// first half of k_hash_sets_pair: XMD, one SSWU map per lane, sum on E2', 3-isogeny; the cofactor clearing follows
+// as a program (fpprog.hpp build_g2_clear_cofactor)
+__global__ void BLS_LB k_hash_map_pair(const sigset *sets, size_t n, fp *hom) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = t >> 1;
+    const bool odd = t & 1;
+    const bool live = i < n;
+    uint8_t msg[32], dst[43];
+    for (int k = 0; k < 32; k++) msg[k] = live ? sets[i].msg[k] : 0;
+    for (int k = 0; k < 43; k++) dst[k] = DST_ETH2[k];
+    fp2 u0, u1;
+    hash_to_field_fp2x2(u0, u1, msg, 32, dst, 43);
+    g2_jac q, other;
+    sswu_g2(q, odd ? u1 : u0);
+    {
+        uint32_t *d = (uint32_t *)&other;
+        const uint32_t *sp = (const uint32_t *)&q;
+        for (int k = 0; k < (int)(sizeof(g2_jac) / 4); k++) d[k] = __shfl_down_sync(0xffffffffu, sp[k], 1);
+    }
+    if (odd || !live) return;
+    pt_add(q, q, other, &SSWU_A);
+    iso3_g2(q, q);
+    g2_jac_to_hom(hom + 6 * i, q);
+}
+// homogeneous (X : Y : Z) -> Jacobian (X Z, Y Z^2, Z); Z = 0 -> infinity
+__global__ void k_g2_hom_to_jac(const fp *hom, size_t n, g2_jac *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fp *h = hom + 6 * i;
+    fp2 X, Y, Z;
+    X.c0 = h[0]; X.c1 = h[1]; Y.c0 = h[2]; Y.c1 = h[3]; Z.c0 = h[4]; Z.c1 = h[5];
+    g2_jac j;
+    if (fp2_is_zero(Z)) pt_set_inf(j);
+    else { fp2 z2; fp2_mul(j.x, X, Z); fp2_sqr(z2, Z); fp2_mul(j.y, Y, z2); j.z = Z; }
+    out[i] = j;
+}
+// inputs of the [r_i] sig_i program (build_g2_mul64): the signature as (x : y : 1) (infinity (0 : 1 : 0)) and the 64
+// scalar bits as field elements 0 / 1
+__global__ void k_g2_mul_prep(const sigset *sets, const uint64_t *r, size_t n, fp *hom, fp *bits) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = t >> 6;
+    const int b = (int)(t & 63);
+    if (i >= n) return;
+    fp v;
+    if ((r[i] >> b) & 1) v = FP_ONE; else fp_set_zero(v);
+    bits[64 * i + b] = v;
+    if (b == 0) {
+        g2_aff a = sets[i].sig;
+        g2_jac j;
+        pt_from_affine(j, a);
+        g2_jac_to_hom(hom + 6 * i, j);
+    }
+}
+
 __global__ void BLS_LB k_g1_mul(const sigset *sets, const uint64_t *r, size_t n, g1_jac *Pj, int *flags) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -438,10 +507,17 @@ __global__ void k_copy_flag(const int *src, int *dst) {
 // operation l.  A slot written
 // in round r is never read in round r (fpprog.hpp frees slots only after their last reading round), so one warp
 // barrier per round orders everything.
-__global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst, fp *out0) {
+// One warp per block; block b runs the program on instance b: in0 + b * s_in0, in1 + b * s_in1, out0 + b * s_out
+// (strides in field elements; the per-batch tails launch one block with zero strides, the small-batch route one block
+// per signature set).
+__global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst, fp *out0,
+                                                   size_t s_in0, size_t s_in1, size_t s_out) {
     extern __shared__ uint4 sm4[];
     fp *slots = (fp *)sm4;
     const int lane = threadIdx.x;
+    in0 += (size_t)blockIdx.x * s_in0;
+    if (in1) in1 += (size_t)blockIdx.x * s_in1;
+    out0 += (size_t)blockIdx.x * s_out;
     const uint32_t nr = prog[0], nin = prog[2], nout = prog[3];
     if (lane == 0) fp_set_zero(slots[0]);
     for (uint32_t e = lane; e < nin; e += 32) {

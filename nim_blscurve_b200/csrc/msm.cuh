@@ -567,7 +567,7 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
                 if (hp.d) {
                     fp *hom = (fp *)(st.buf + o_hom);
                     k_msm_horner_prep<<<1, 128, 0, ts>>>(sg, nseg, nwin, hom);
-                    k_fp_program<<<1, 32, (size_t)hp.nslots * sizeof(fp), ts>>>(hp.d, hom, nullptr, nullptr, hom + 3 * nwin);
+                    k_fp_program<<<1, 32, (size_t)hp.nslots * sizeof(fp), ts>>>(hp.d, hom, nullptr, nullptr, hom + 3 * nwin, 0, 0, 0);
                     k_msm_horner_finish<<<1, 32, 0, ts>>>(hom + 3 * nwin, d_out_jac, d_out_aff);
                     nl += 3;
                     programmed = true;

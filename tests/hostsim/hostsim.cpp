@@ -126,6 +126,10 @@ static void const_pool(fp *cst) {
     memcpy(cst + fpprog::CONST_FROB1, FROB1, sizeof(FROB1));
     memcpy(cst + fpprog::CONST_FROB2, FROB2, sizeof(FROB2));
     memcpy(cst + fpprog::CONST_FROB3, FROB3, sizeof(FROB3));
+    memcpy(cst + fpprog::CONST_PSI_CX, &PSI_CX, sizeof(PSI_CX));
+    memcpy(cst + fpprog::CONST_PSI_CY, &PSI_CY, sizeof(PSI_CY));
+    memcpy(cst + fpprog::CONST_PSI2_CX, &PSI2_CX, sizeof(PSI2_CX));
+    memcpy(cst + fpprog::CONST_ONE, &FP_ONE, sizeof(FP_ONE));
 }
 // stats[0..3] = rounds, mul rounds, slots, ops
 int hs_prog_final(const fp12 *partials, int count, fp12 *out, int *stats) {
@@ -166,6 +170,26 @@ int hs_prog_msm_horner(const fp *hom, int nwin, int c, fp *out5, int *stats) {
     fpprog::Program P = fpprog::build_msm_horner_g1(nwin, c);
     if (!P.ok) return 0;
     run_program(P.words, hom, nullptr, nullptr, out5);
+    stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
+    return 1;
+}
+// per-set G2 programs of the small-batch route: hom = (X, Y, Z) over Fp2 = 6 fp in, 6 fp out
+int hs_prog_g2_clear_cofactor(const fp *hom, fp *out6, int *stats) {
+    fpprog::Program P = fpprog::build_g2_clear_cofactor();
+    if (!P.ok) return 0;
+    fp cst[fpprog::CONST_COUNT];
+    const_pool(cst);
+    run_program(P.words, hom, nullptr, cst, out6);
+    stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
+    return 1;
+}
+int hs_prog_g2_mul64(const fp *hom, uint64_t k, fp *out6, int *stats) {
+    fpprog::Program P = fpprog::build_g2_mul64();
+    if (!P.ok) return 0;
+    fp cst[fpprog::CONST_COUNT], bits[64];
+    const_pool(cst);
+    for (int i = 0; i < 64; i++) { if ((k >> i) & 1) bits[i] = FP_ONE; else fp_set_zero(bits[i]); }
+    run_program(P.words, hom, bits, cst, out6);
     stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
     return 1;
 }

@@ -236,6 +236,56 @@ def test_msm_horner_program(hs):
         assert stats[2] <= 1024, list(stats)
 
 
+def _g2_hom_bytes(pt, rng):
+    """affine G2 point (or None) -> 6 Montgomery fp of a random homogeneous representative"""
+    if pt is None:
+        x, y, z = (0, 0), (rng.randrange(1, P), rng.randrange(P)), (0, 0)
+    else:
+        k = (rng.randrange(1, P), rng.randrange(P))
+        x, y, z = pr.f2_mul(pt[0], k), pr.f2_mul(pt[1], k), k
+    return b"".join(pr.fp_to_mont_bytes(c) for v in (x, y, z) for c in v)
+
+
+def _g2_from_hom(raw):
+    v = [pr.fp_from_mont_bytes(raw[48 * i:48 * i + 48]) for i in range(6)]
+    z = (v[4], v[5])
+    if z == (0, 0):
+        return None
+    zi = pr.f2_inv(z)
+    return pr.f2_mul((v[0], v[1]), zi), pr.f2_mul((v[2], v[3]), zi)
+
+
+def test_g2_programs(hs):
+    """fpprog.hpp build_g2_clear_cofactor / build_g2_mul64 (complete projective formulas on the twist, one warp per set
+    on the device) against pyref: cofactor clearing of points on E2 outside the subgroup, 64-bit multiples incl. edge
+    scalars, the point at infinity."""
+    rng = random.Random(33)
+    stats = (C.c_int * 4)()
+    # points on E2 (not in G2): x random, y = sqrt(x^3 + 4(1+u))
+    pts = []
+    while len(pts) < 3:
+        x = (rng.randrange(P), rng.randrange(P))
+        rhs = pr.f2_add(pr.f2_mul(pr.f2_sqr(x), x), (4, 4))
+        if pr.f2_is_square(rhs):
+            pts.append((x, pr.f2_sqrt(rhs)))
+    for pt in pts + [None]:
+        r = out(6 * 48)
+        assert hs.hs_prog_g2_clear_cofactor(buf(_g2_hom_bytes(pt, rng)), r, stats) == 1
+        exp = pr.g2_clear_cofactor(pt) if pt is not None else None
+        assert _g2_from_hom(bytes(r)) == exp
+        assert stats[2] <= 1024, list(stats)
+    g = pr.G2_GEN
+    q = pr.g2_mul(g, 987654321)
+    for k in [1, 2, 3, 0x8000000000000000, 0xffffffffffffffff, 0x5555555555555555] + [rng.getrandbits(64) for _ in range(4)]:
+        r = out(6 * 48)
+        assert hs.hs_prog_g2_mul64(buf(_g2_hom_bytes(q, rng)), C.c_uint64(k), r, stats) == 1
+        assert _g2_from_hom(bytes(r)) == pr.g2_mul(q, k), hex(k)
+    r = out(6 * 48)
+    assert hs.hs_prog_g2_mul64(buf(_g2_hom_bytes(None, rng)), C.c_uint64(12345), r, stats) == 1
+    assert _g2_from_hom(bytes(r)) is None
+    assert stats[2] <= 1024, list(stats)
+
+
 def test_g1_mul_windowed(hs):
     """pt_mul_u64_w4 (signed 4-bit windows) == pt_mul_u64 (double-and-add) == pyref, incl. edge scalars and infinity."""
     rng = random.Random(5)
