@@ -59,6 +59,7 @@ struct blsgpu_ctx {
     // warp-cooperative tail programs (fpprog.hpp), compiled on first use and kept on the device
     struct dev_prog { uint32_t *d = nullptr; int nslots = 0, nrounds = 0; };
     std::map<int, dev_prog> combine_progs, final_progs, norm_progs, set_progs;   // keyed by segment count / partial count
+    fp *d_small_lines = nullptr;                             // 68 x 6 field elements per pair (small-batch route)
     fp *d_small = nullptr;                                   // per-set program inputs/outputs of the small-batch route
     fp *d_norm = nullptr;                                    // [0] Fp norm taken out of the final exponentiation, [1] its inverse
     fp *d_consts = nullptr;                                  // Frobenius coefficients (fpprog::CONST_*)
@@ -104,7 +105,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     for (auto &kv : ctx->final_progs) cudaFree(kv.second.d);
     for (auto &kv : ctx->norm_progs) cudaFree(kv.second.d);
     for (auto &kv : ctx->set_progs) cudaFree(kv.second.d);
-    cudaFree(ctx->d_norm); cudaFree(ctx->d_small); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
+    cudaFree(ctx->d_norm); cudaFree(ctx->d_small); cudaFree(ctx->d_small_lines); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2 * ST_COUNT + 3; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
@@ -231,7 +232,7 @@ static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size
     return 0;
 }
 
-enum { SETPROG_COFACTOR = 0, SETPROG_G2MUL64 = 1 };
+enum { SETPROG_COFACTOR = 0, SETPROG_G2MUL64 = 1, SETPROG_LINES = 2 };
 
 // Compile (once) and fetch a tail program; kind 0 = combine over `key` segments, 1 = final exponentiation of `key`
 // partials with the Fp inversion supplied in IN1, 2 = the norm that inversion applies to (fpprog.hpp build_final),
@@ -246,7 +247,7 @@ static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &ou
         for (int j = 0; j < key; j++) len[j] = ml_seg_hi(j, key) - ml_seg_lo(j, key) + 1;
         P = fpprog::build_combine(key, len);
     } else if (kind == 3) {                              // per-set programs of the small-batch route
-        P = key == SETPROG_COFACTOR ? fpprog::build_g2_clear_cofactor() : fpprog::build_g2_mul64();
+        P = key == SETPROG_COFACTOR ? fpprog::build_g2_clear_cofactor() : (key == SETPROG_G2MUL64 ? fpprog::build_g2_mul64() : fpprog::build_miller_lines());
     } else {
         P = fpprog::build_final(key, kind == 1 ? fpprog::INV_EXTERNAL : fpprog::INV_EMIT_ARG);
     }
@@ -346,7 +347,22 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
     for (size_t off = 0; off < np; off += ctx->lines_cap) {
         size_t t = np - off < ctx->lines_cap ? np - off : ctx->lines_cap;
         size_t stride = ctx->lines_cap;
-        k_miller_lines<<<nblk(t), 128, 0, s>>>(ctx->d_Q + off, ctx->d_P + off, t, ctx->d_lines, stride);
+        static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 7;   // bit 2: lines
+        if ((small_env & 4) && single && np <= SMALL_ROUTE_MAX + 1 && !ctx->serial_tail) {
+            // one warp per pair runs the 68 line evaluations as a dataflow program (two multiplication levels per
+            // tangent instead of ~20 dependent products), then a scatter into the accumulation's layout
+            blsgpu_ctx::dev_prog lp;
+            rc = get_prog(ctx, 3, SETPROG_LINES, lp);
+            if (rc) return rc;
+            const size_t per = (size_t)ML_NLINES * 6;
+            if (!ctx->d_small_lines) CK(cudaMalloc((void **)&ctx->d_small_lines, (size_t)(SMALL_ROUTE_MAX + 1) * per * sizeof(fp)));
+            launch_prog_many(ctx, lp, s, t, (const fp *)ctx->d_Q, 4, (const fp *)ctx->d_P, 2, ctx->d_small_lines, per);
+            k_lines_from_prog<<<nblk(t * ML_NLINES * ML_LINE_WORDS, 256), 256, 0, s>>>((const uint32_t *)ctx->d_small_lines, ctx->d_Q, ctx->d_P, t,
+                                                                                      ctx->d_lines, stride);
+            ctx->launches++;
+        } else {
+            k_miller_lines<<<nblk(t), 128, 0, s>>>(ctx->d_Q + off, ctx->d_P + off, t, ctx->d_lines, stride);
+        }
         if (single) { END(ST_LINES, s); BEGIN(ST_ACC, s); }
         size_t ngroups = (t + G - 1) / G;
         if (team) {
@@ -417,7 +433,7 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     }
     // Small-batch route: the serial stretches of a set (cofactor clearing, [r_i] sig_i) run as per-set dataflow
     // programs, one warp per set (fpprog.hpp build_g2_clear_cofactor / build_g2_mul64)
-    static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 3;   // bit 0 hash, bit 1 sig
+    static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 7;   // bit 0 hash, bit 1 sig (bit 2: lines, run_miller)
     const bool small = small_env != 0 && n <= SMALL_ROUTE_MAX && !ctx->serial_tail;
     const bool small_hash = small && (small_env & 1), small_sig = small && (small_env & 2);
     blsgpu_ctx::dev_prog p_cof, p_mul;

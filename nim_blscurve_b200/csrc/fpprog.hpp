@@ -492,4 +492,68 @@ inline Program build_g2_mul64() {
     return compile(b);
 }
 
+// All 68 line triples of one Miller-loop pair (pairing.cuh miller_lines: 63 tangents + 5 chords in execution order, each
+// already scaled by (-x_P, y_P)), the same formulas traced over V2.  IN0[0..3] = Q affine (x.re, x.im, y.re, y.im),
+// IN1[0..1] = P affine (x, y); OUT0[6 s .. 6 s + 5] = (l0.re, l0.im, l1.re, l1.im, l2.re, l2.im) of line s.
+// The caller substitutes the neutral line for pairs with a point at infinity (no branches in a dataflow program).
+struct TP { V2 x, y, z; };
+inline V2 mul3(V2 a) { return dbl(a) + a; }
+inline void line_dbl_t(TP &T, V2 &l0, V2 &l1, V2 &l2) {                 // line_dbl_proj
+    V2 B = sqr(T.y), C = sqr(T.z), J = sqr(T.x);
+    V2 A2 = sqr(T.x + T.y) - J - B;
+    V2 H = sqr(T.y + T.z) - B - C;
+    V2 E = mul3(dbl(dbl(mul_xi(C))));
+    V2 F = mul3(E);
+    l0 = B - E;
+    l1 = mul3(J);
+    l2 = H;
+    V2 nx = A2 * (B - F);
+    V2 ny = sqr(B + F) - mul3(sqr(dbl(E)));
+    V2 nz = dbl(dbl(B * H));
+    T = {nx, ny, nz};
+}
+inline void line_add_t(TP &T, V2 qx, V2 qy, V2 &l0, V2 &l1, V2 &l2) {   // line_add_proj
+    V2 th = T.y - qy * T.z, la = T.x - qx * T.z;
+    V2 c = sqr(th), d = sqr(la);
+    V2 e = la * d, f = T.z * c, g = T.x * d;
+    V2 h = e + f - g - g;
+    V2 nx = la * h, ny = th * (g - h) - e * T.y, nz = T.z * e;
+    l0 = th * qx - la * qy;
+    l1 = th;
+    l2 = la;
+    T = {nx, ny, nz};
+}
+inline Program build_miller_lines() {
+    Builder b;
+    g_b = &b;
+    V2 qx = {{b.leaf(BUF_IN0, 0)}, {b.leaf(BUF_IN0, 1)}}, qy = {{b.leaf(BUF_IN0, 2)}, {b.leaf(BUF_IN0, 3)}};
+    V px = {b.leaf(BUF_IN1, 0)}, py = {b.leaf(BUF_IN1, 1)};
+    V npx = vneg(px);
+    V2 one = {{b.leaf(BUF_CONST, CONST_ONE)}, vzero()};
+    TP T = {qx, qy, one};
+    int s = 0;
+    auto emit = [&](V2 l0, V2 l1, V2 l2) {
+        l1 = mul_fp(l1, npx);
+        l2 = mul_fp(l2, py);
+        V2 c[3] = {l0, l1, l2};
+        for (int k = 0; k < 3; k++) {
+            // outputs must be computed nodes or leaves with their own slot; "+ 0" folds away, so route through the table
+            b.output(c[k].c0.id, BUF_OUT0, 6 * s + 2 * k);
+            b.output(c[k].c1.id, BUF_OUT0, 6 * s + 2 * k + 1);
+        }
+        s++;
+    };
+    for (int i = 62; i >= 0; i--) {
+        V2 l0, l1, l2;
+        line_dbl_t(T, l0, l1, l2);
+        emit(l0, l1, l2);
+        if ((Z_ABS >> i) & 1) {
+            line_add_t(T, qx, qy, l0, l1, l2);
+            emit(l0, l1, l2);
+        }
+    }
+    g_b = nullptr;
+    return compile(b);
+}
+
 }  // namespace fpprog

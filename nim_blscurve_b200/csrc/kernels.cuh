@@ -355,6 +355,25 @@ __global__ void __launch_bounds__(128, BLS_LINES_BLOCKS) k_miller_lines(const g2
     miller_lines(q, a, lines + p, stride);
 }
 
+// Small-batch route: the lines come out of the per-pair program (fpprog.hpp build_miller_lines) as 68 x 6 field
+// elements per pair; scatter them into the word-major layout the accumulation reads, substituting the neutral line
+// (1, 0, 0) for pairs with a point at infinity (pairing.c:233-241), which the branch-free program cannot express.
+__global__ void k_lines_from_prog(const uint32_t *prog_out, const g2_aff *Q, const g1_aff *P, size_t np, uint32_t *lines,
+                                  size_t stride) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = (size_t)ML_NLINES * ML_LINE_WORDS;
+    if (t >= np * per) return;
+    const size_t p = t % np, sw = t / np;
+    uint32_t v;
+    if (aff_is_inf(Q[p]) | aff_is_inf(P[p])) {
+        const int w = (int)(sw % ML_LINE_WORDS);
+        v = w < 12 ? FP_ONE.l[w] : 0u;
+    } else {
+        v = prog_out[p * per + sw];
+    }
+    lines[sw * stride + p] = v;
+}
+
 #define BLS_ACC_BS 128
 #ifndef BLS_ACC_BLOCKS
 #define BLS_ACC_BLOCKS 2

@@ -193,6 +193,18 @@ int hs_prog_g2_mul64(const fp *hom, uint64_t k, fp *out6, int *stats) {
     stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
     return 1;
 }
+// Miller-loop lines of one pair: the per-pair program against the straight-line miller_lines of pairing.cuh.
+// out_prog: 68 x 6 fp; out_ref: 68 x 72 words (stride 1)
+int hs_prog_miller_lines(const g2_aff *Q, const g1_aff *P, fp *out_prog, uint32_t *out_ref, int *stats) {
+    fpprog::Program Pg = fpprog::build_miller_lines();
+    if (!Pg.ok) return 0;
+    fp cst[fpprog::CONST_COUNT];
+    const_pool(cst);
+    run_program(Pg.words, (const fp *)Q, (const fp *)P, cst, out_prog);
+    miller_lines(*Q, *P, out_ref, 1);
+    stats[0] = Pg.nrounds; stats[1] = Pg.nmul_rounds; stats[2] = Pg.nslots; stats[3] = Pg.nops;
+    return 1;
+}
 int hs_pubkey_from_bytes(const uint8_t *in, int len, int group_check, g1_aff *out) { return pubkey_from_bytes(*out, in, len, group_check != 0); }
 int hs_signature_from_bytes(const uint8_t *in, int len, int group_check, g2_aff *out) { return signature_from_bytes(*out, in, len, group_check != 0); }
 void hs_g1_compress(const g1_aff *p, uint8_t *out) { g1_compress(out, *p); }

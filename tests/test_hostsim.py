@@ -286,6 +286,20 @@ def test_g2_programs(hs):
     assert stats[2] <= 1024, list(stats)
 
 
+def test_miller_lines_program(hs):
+    """fpprog.hpp build_miller_lines == pairing.cuh miller_lines, word for word (every Fp value is canonical, so equal
+    formulas give equal bits): 68 line triples of a pair, for several (Q, P)."""
+    rng = random.Random(44)
+    stats = (C.c_int * 4)()
+    for _ in range(3):
+        q = pr.g2_mul(pr.G2_GEN, rng.randrange(1, 1 << 200))
+        pt = pr.g1_mul(pr.G1_GEN, rng.randrange(1, 1 << 200))
+        o1, o2 = out(68 * 6 * 48), out(68 * 72 * 4)
+        assert hs.hs_prog_miller_lines(buf(pr.g2_to_mem(q)), buf(pr.g1_to_mem(pt)), o1, o2, stats) == 1
+        assert bytes(o1) == bytes(o2)
+        assert stats[2] <= 1024, list(stats)
+
+
 def test_g1_mul_windowed(hs):
     """pt_mul_u64_w4 (signed 4-bit windows) == pt_mul_u64 (double-and-add) == pyref, incl. edge scalars and infinity."""
     rng = random.Random(5)
