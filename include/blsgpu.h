@@ -178,7 +178,7 @@ int blsgpu_last_launches(const blsgpu_ctx *ctx);
 /* Fp unit ops on the device: op 0=mul 1=add 2=sub 3=sqr 4=inverse; a,b,out: n x 48 bytes (Montgomery). */
 int blsgpu_test_fp(blsgpu_ctx *ctx, int op, const void *a, const void *b, size_t n, void *out);
 /* The message hash of the small-batch route (two-lane map kernel, then the cofactor-clearing dataflow program):
- * n <= 1024 sets in (host, 320 B each); out_in / out_out (nullable): n x 6 field elements (48 B each, Montgomery) =
+ * n <= 4096 sets in (host, 320 B each); out_in / out_out (nullable): n x 6 field elements (48 B each, Montgomery) =
  * the homogeneous E2 point (X : Y : Z) before / after the program.  H(m_i) = (X/Z, Y/Z) of out_out. */
 int blsgpu_test_small_hash(blsgpu_ctx *ctx, const void *sets320, size_t n, uint8_t *out_in, uint8_t *out_out);
 /* Integer-multiply pipe microbenchmark: returns measured 32x32->64 multiply-accumulates per second. */

@@ -283,7 +283,19 @@ static int launch_prog_many(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, cuda
     return 0;
 }
 
-#define SMALL_ROUTE_MAX 1024            // sets; beyond this a warp per set no longer fits the machine in one wave
+// Largest batches that take the warp-per-set programs: the cofactor / [r]sig programs (5-6 KB of shared memory per
+// warp, 32 warps per SM) up to SMALL_ROUTE_MAX sets, the lines program (33 KB per warp, 6 per SM) up to SMALL_LINES_MAX
+// pairs; beyond that a thread per set fills the machine better (tools/probe.py, profiles/).
+#define SMALL_ROUTE_CAP 4096
+static size_t small_route_max() {
+    static const size_t v = getenv("BLSGPU_SMALL_MAX") ? (size_t)atoll(getenv("BLSGPU_SMALL_MAX")) : 4096;
+    return v > SMALL_ROUTE_CAP ? SMALL_ROUTE_CAP : v;
+}
+static size_t small_lines_max() {
+    static const size_t v = getenv("BLSGPU_SMALL_LINES_MAX") ? (size_t)atoll(getenv("BLSGPU_SMALL_LINES_MAX")) : 2049;
+    return v > SMALL_ROUTE_CAP + 1 ? SMALL_ROUTE_CAP + 1 : v;
+}
+#define SMALL_ROUTE_MAX SMALL_ROUTE_CAP   /* buffer strides */
 #define SMALL_FP_PER_SET (6 + 6 + 6 + 6 + 64)
 
 // Work decomposition of the accumulation: G pairs per group (they share the Fp12 squarings) and nseg loop segments,
@@ -348,14 +360,14 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
         size_t t = np - off < ctx->lines_cap ? np - off : ctx->lines_cap;
         size_t stride = ctx->lines_cap;
         static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 7;   // bit 2: lines
-        if ((small_env & 4) && single && np <= SMALL_ROUTE_MAX + 1 && !ctx->serial_tail) {
+        if ((small_env & 4) && single && np <= small_lines_max() && !ctx->serial_tail) {
             // one warp per pair runs the 68 line evaluations as a dataflow program (two multiplication levels per
             // tangent instead of ~20 dependent products), then a scatter into the accumulation's layout
             blsgpu_ctx::dev_prog lp;
             rc = get_prog(ctx, 3, SETPROG_LINES, lp);
             if (rc) return rc;
             const size_t per = (size_t)ML_NLINES * 6;
-            if (!ctx->d_small_lines) CK(cudaMalloc((void **)&ctx->d_small_lines, (size_t)(SMALL_ROUTE_MAX + 1) * per * sizeof(fp)));
+            if (!ctx->d_small_lines) CK(cudaMalloc((void **)&ctx->d_small_lines, small_lines_max() * per * sizeof(fp)));
             launch_prog_many(ctx, lp, s, t, (const fp *)ctx->d_Q, 4, (const fp *)ctx->d_P, 2, ctx->d_small_lines, per);
             k_lines_from_prog<<<nblk(t * ML_NLINES * ML_LINE_WORDS, 256), 256, 0, s>>>((const uint32_t *)ctx->d_small_lines, ctx->d_Q, ctx->d_P, t,
                                                                                       ctx->d_lines, stride);
@@ -434,7 +446,7 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     // Small-batch route: the serial stretches of a set (cofactor clearing, [r_i] sig_i) run as per-set dataflow
     // programs, one warp per set (fpprog.hpp build_g2_clear_cofactor / build_g2_mul64)
     static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 7;   // bit 0 hash, bit 1 sig (bit 2: lines, run_miller)
-    const bool small = small_env != 0 && n <= SMALL_ROUTE_MAX && !ctx->serial_tail;
+    const bool small = small_env != 0 && n <= small_route_max() && !ctx->serial_tail;
     const bool small_hash = small && (small_env & 1), small_sig = small && (small_env & 2);
     blsgpu_ctx::dev_prog p_cof, p_mul;
     fp *sm_hash_in = nullptr, *sm_hash_out = nullptr, *sm_sig_in = nullptr, *sm_sig_out = nullptr, *sm_bits = nullptr;
