@@ -512,9 +512,10 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         END(ST_G1MUL, s);
     }
     BEGIN(ST_AFFINE, s);
-    // a handful of sets: one inversion on one or two threads is pure latency -> binary Euclid (it diverges across the
-    // lanes of a warp, so from a few dozen sets on the uniform Fermat chain is as quick: measured 0.53 vs 0.46 ms at 129)
-    k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, n <= 16 ? 1 : 0);
+    // small batches: one inversion per set is pure latency -> binary Euclid, one working lane per warp (it diverges
+    // across the lanes of a warp: sharing warps it is no quicker than the uniform Fermat chain, 0.53 vs 0.46 ms at 129)
+    if (small) k_pairs_affine<<<(unsigned)n, 32, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 1, 1);
+    else k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 0, 0);
     END(ST_AFFINE, s);
     ctx->launches += 3;
     if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));   // join: pair number n is in place
