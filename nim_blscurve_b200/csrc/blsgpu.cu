@@ -304,7 +304,7 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
     if (team && np <= 8192) {
         // Latency regime (the machine is not full).  Measured on B200 (tools/gpu_small_sweep.sh): a team spends ~7.5 us
         // per (squaring or line) step while all teams are resident (~12k of them), the product over groups is one
-        // block-wide tree (0.59 ms) up to 128 groups and two launches (1.16 ms) beyond, the segment Horner program costs
+        // block-wide tree (0.59 ms) up to 128 groups and two launches (1.16 ms) beyond (0.084 ms per tree level), the segment Horner program costs
         // 0.22 ms + 7.4 us per segment.
         double best = 0.0;
         G = 1; nseg = 32;
@@ -313,7 +313,9 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
                 const size_t ngroups = (np + g - 1) / g;
                 const double waves = (double)((ngroups * ns + 11999) / 12000);
                 const double acc = waves * (double)((63 + ns - 1) / ns) * (1 + g) * 7.5e-3;
-                const double cost = acc + (ngroups <= 128 ? 0.59 : 1.16) + 0.22 + 7.4e-3 * ns;
+                int depth = 0;
+                while (((size_t)1 << depth) < ngroups) depth++;
+                const double cost = acc + (ngroups <= 128 ? 0.084 * depth : 1.16) + 0.22 + 7.4e-3 * ns;
                 if (best == 0.0 || cost < best) { best = cost; G = g; nseg = ns; }
             }
     } else if (team) {                             // ~32k teams: 6 lanes each, squarings are cheap to share widely
@@ -783,7 +785,21 @@ static int verify_pairs_dev(blsgpu_ctx *ctx, const g1_aff *d_pks, size_t n, cons
     ctx->launches = 0;
     CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
     BEGIN(ST_HASH, s);
-    k_hash_to_g2<<<nblk(n), 128, 0, s>>>(d_msgs, n, 0, d_offs, d_dst, (uint32_t)dst_len, ctx->d_Q, nullptr);
+    static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 7;
+    if ((small_env & 1) && n <= small_route_max() && !ctx->serial_tail) {
+        // small-batch route (see run_partial): two lanes per message, cofactor clearing as a per-message program
+        blsgpu_ctx::dev_prog p_cof;
+        int rcp = get_prog(ctx, 3, SETPROG_COFACTOR, p_cof);
+        if (rcp) return rcp;
+        if (!ctx->d_small) CK(cudaMalloc((void **)&ctx->d_small, (size_t)SMALL_ROUTE_MAX * SMALL_FP_PER_SET * sizeof(fp)));
+        fp *hin = ctx->d_small, *hout = hin + 6 * SMALL_ROUTE_MAX;
+        k_hash_map_pair_msgs<<<nblk(2 * n), 128, 0, s>>>(d_msgs, d_offs, d_dst, (uint32_t)dst_len, n, hin);
+        launch_prog_many(ctx, p_cof, s, n, hin, 6, nullptr, 0, hout, 6);
+        k_g2_hom_to_affine<<<(unsigned)n, 32, 0, s>>>(hout, n, ctx->d_Q);
+        ctx->launches += 2;
+    } else {
+        k_hash_to_g2<<<nblk(n), 128, 0, s>>>(d_msgs, n, 0, d_offs, d_dst, (uint32_t)dst_len, ctx->d_Q, nullptr);
+    }
     END(ST_HASH, s);
     k_verify_pairs<<<nblk(n + 1), 128, 0, s>>>(d_pks, n, d_sig, ctx->d_Q, ctx->d_P, ctx->d_flags);
     ctx->launches += 2;

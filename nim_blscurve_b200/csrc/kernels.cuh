@@ -197,6 +197,40 @@ __global__ void BLS_LB k_hash_map_pair(const sigset *sets, size_t n, fp *hom) {
     iso3_g2(q, q);
     g2_jac_to_hom(hom + 6 * i, q);
 }
+// the same for the verify entry points: arbitrary messages (msgs + offs[i] .. offs[i+1]) and domain separation tag
+__global__ void BLS_LB k_hash_map_pair_msgs(const uint8_t *msgs, const uint32_t *offs, const uint8_t *dst, uint32_t dst_len,
+                                            size_t n, fp *hom) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = t >> 1;
+    const bool odd = t & 1;
+    const bool live = i < n;
+    const size_t j = live ? i : 0;
+    fp2 u0, u1;
+    hash_to_field_fp2x2(u0, u1, msgs + offs[j], offs[j + 1] - offs[j], dst, dst_len);
+    g2_jac q, other;
+    sswu_g2(q, odd ? u1 : u0);
+    {
+        uint32_t *d = (uint32_t *)&other;
+        const uint32_t *sp = (const uint32_t *)&q;
+        for (int k = 0; k < (int)(sizeof(g2_jac) / 4); k++) d[k] = __shfl_down_sync(0xffffffffu, sp[k], 1);
+    }
+    if (odd || !live) return;
+    pt_add(q, q, other, &SSWU_A);
+    iso3_g2(q, q);
+    g2_jac_to_hom(hom + 6 * i, q);
+}
+// homogeneous (X : Y : Z) -> affine (X / Z, Y / Z), one working lane per warp-sized block (binary-Euclid inversion)
+__global__ void k_g2_hom_to_affine(const fp *hom, size_t n, g2_aff *out) {
+    if (threadIdx.x != 0 || blockIdx.x >= n) return;
+    const fp *h = hom + 6 * (size_t)blockIdx.x;
+    fp2 X, Y, Z, zi;
+    X.c0 = h[0]; X.c1 = h[1]; Y.c0 = h[2]; Y.c1 = h[3]; Z.c0 = h[4]; Z.c1 = h[5];
+    g2_aff a;
+    fp2_inv_vartime(zi, Z);                 // Z = 0 -> 0 -> the all-zero affine encoding of infinity
+    fp2_mul(a.x, X, zi);
+    fp2_mul(a.y, Y, zi);
+    out[blockIdx.x] = a;
+}
 // homogeneous (X : Y : Z) -> Jacobian (X Z, Y Z^2, Z); Z = 0 -> infinity
 __global__ void k_g2_hom_to_jac(const fp *hom, size_t n, g2_jac *out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,9 +420,13 @@ __global__ void k_lines_from_prog(const uint32_t *prog_out, const g2_aff *Q, con
 #define BLS_ACC_BLOCKS 2
 #endif
 // product of the block's Fp12 values through shared memory (word-major, conflict-free); result in thread 0
-__device__ __forceinline__ void block_fp12_product(fp12 &f, uint32_t *sm) {
+// `live` = number of threads holding a value other than one (they are the lowest thread indices): the tree starts at
+// the smallest power of two that covers them, so a batch of a few pairs does not pay seven levels of products by one
+__device__ __forceinline__ void block_fp12_product(fp12 &f, uint32_t *sm, int live = BLS_ACC_BS) {
     const int tid = threadIdx.x;
-    for (int half = BLS_ACC_BS / 2; half >= 1; half >>= 1) {
+    int top = BLS_ACC_BS / 2;
+    while (top >= 1 && top >= live) top >>= 1;
+    for (int half = top; half >= 1; half >>= 1) {
         if (tid >= half && tid < 2 * half) {
             const uint32_t *w = (const uint32_t *)&f;
             for (int k = 0; k < 144; k++) sm[k * half + (tid - half)] = w[k];
@@ -503,7 +541,7 @@ __global__ void __launch_bounds__(BLS_ACC_BS, BLS_ACC_BLOCKS) k_fp12_rows(const 
         fp12 b = row[c];
         if (have) fp12_mul(f, f, b); else { f = b; have = true; }
     }
-    block_fp12_product(f, sm);
+    block_fp12_product(f, sm, ncols < BLS_ACC_BS ? (int)ncols : BLS_ACC_BS);
     if (threadIdx.x == 0) seg[blockIdx.x] = f;
 }
 
