@@ -311,6 +311,7 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
         for (int g = 1; g <= 64; g *= 2)
             for (int ns = 4; ns <= 32; ns *= 2) {
                 const size_t ngroups = (np + g - 1) / g;
+                if (ngroups * ns > 32768) continue;             // d_F holds at least 40 000 (group, segment) products
                 const double waves = (double)((ngroups * ns + 11999) / 12000);
                 const double acc = waves * (double)((63 + ns - 1) / ns) * (1 + g) * 7.5e-3;
                 int depth = 0;

@@ -126,3 +126,22 @@ def test_epoch_batch_full_size_properties(br, srb):
         assert big.verify_raw(window, srb, 16, want_gt=True) == br.batch_verify(window, srb, 16)
     finally:
         big.close()
+
+
+@pytest.mark.parametrize("n", [4097, 6000, 9000])
+def test_route_boundaries_vs_blst(br, srb, n):
+    """The batch pipeline picks its kernels by batch size (warp-per-set programs up to 4 096 sets, two lanes per message
+    up to 8 192, a thread per set beyond; the G2 sum switches to Pippenger at 2 048): one batch just past each boundary,
+    valid and with one corrupted set, verdict and GT against BLST."""
+    import nim_blscurve_b200 as bg
+    c = bg.BatchedBLSVerifierCache(max_sets=n, device=0)
+    try:
+        out = (C.c_uint8 * (320 * n))()
+        assert bg.lib().blsgpu_make_sets(c.handle, 31337, 0, n, out, 0) == 0
+        sets = bytes(out)
+        assert c.verify_raw(sets, srb, 32) is True
+        bad = bytearray(sets)
+        bad[(n // 2) * 320 + 100] ^= 0x10         # message of one set (points stay on the curve: inputs are pre-validated)
+        assert c.verify_raw(bytes(bad), srb, 32, want_gt=True) == br.batch_verify(bytes(bad), srb, 32)
+    finally:
+        c.close()
