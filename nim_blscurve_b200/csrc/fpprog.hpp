@@ -68,12 +68,25 @@ inline V2 neg(V2 a) { return {vneg(a.c0), vneg(a.c1)}; }
 inline V2 dbl(V2 a) { return a + a; }
 inline V2 conj(V2 a) { return {a.c0, vneg(a.c1)}; }
 inline V2 mul_xi(V2 a) { return {a.c0 - a.c1, a.c0 + a.c1}; }          // * (1+u)
-inline V2 operator*(V2 a, V2 b) {                                       // Karatsuba, as fp2_mul
-    V t2 = (a.c0 + a.c1) * (b.c0 + b.c1), t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
+// Shallow mode (per-set G2 / line programs): a warp has lanes to spare there, so Fp2 products are taken schoolbook
+// (4 multiplications, one addition level after) and squares as a0^2, a1^2, a0 a1 — one multiplication more than
+// Karatsuba / complex squaring but two addition levels fewer per product on the critical path.  Results are the same
+// field elements (every value is canonical), only the schedule changes.
+static thread_local bool g_fp2_shallow = false;
+inline V2 operator*(V2 a, V2 b) {
+    if (g_fp2_shallow) {
+        V t0 = a.c0 * b.c0, t1 = a.c1 * b.c1, t2 = a.c0 * b.c1, t3 = a.c1 * b.c0;
+        return {t0 - t1, t2 + t3};
+    }
+    V t2 = (a.c0 + a.c1) * (b.c0 + b.c1), t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;      // Karatsuba, as fp2_mul
     return {t0 - t1, t2 - t0 - t1};
 }
-inline V2 sqr(V2 a) {                                                   // as fp2_sqr
-    V t = a.c0 * a.c1;
+inline V2 sqr(V2 a) {
+    if (g_fp2_shallow) {
+        V s0 = a.c0 * a.c0, s1 = a.c1 * a.c1, t = a.c0 * a.c1;
+        return {s0 - s1, t + t};
+    }
+    V t = a.c0 * a.c1;                                                  // as fp2_sqr
     return {(a.c0 + a.c1) * (a.c0 - a.c1), t + t};
 }
 inline V2 mul_fp(V2 a, V k) { return {a.c0 * k, a.c1 * k}; }
@@ -459,6 +472,7 @@ inline PT<V2> g2_mul_by_x(PT<V2> p) {
 inline Program build_g2_clear_cofactor() {
     Builder b;
     g_b = &b;
+    g_fp2_shallow = true;
     PT<V2> p = load_g2(BUF_IN0, 0);
     PT<V2> t1 = g2_mul_by_x(p);
     PT<V2> t2 = g2_psi(p);
@@ -469,6 +483,7 @@ inline Program build_g2_clear_cofactor() {
     t3 = rcb_add(t3, rcb_neg(t1));
     store_g2(rcb_add(t3, rcb_neg(p)), BUF_OUT0, 0);
     g_b = nullptr;
+    g_fp2_shallow = false;
     return compile(b);
 }
 // [k]Q for a 64-bit k given as 64 field elements 0 / 1 (IN1[0..63], least significant first; Montgomery form), Q
@@ -477,6 +492,7 @@ inline Program build_g2_clear_cofactor() {
 inline Program build_g2_mul64() {
     Builder b;
     g_b = &b;
+    g_fp2_shallow = true;
     PT<V2> q = load_g2(BUF_IN0, 0);
     V one = {b.leaf(BUF_CONST, CONST_ONE)};
     auto addend = [&](int bit) {
@@ -489,6 +505,7 @@ inline Program build_g2_mul64() {
     for (int i = 62; i >= 0; i--) acc = rcb_add(rcb_dbl(acc), addend(i));
     store_g2(acc, BUF_OUT0, 0);
     g_b = nullptr;
+    g_fp2_shallow = false;
     return compile(b);
 }
 
@@ -526,6 +543,7 @@ inline void line_add_t(TP &T, V2 qx, V2 qy, V2 &l0, V2 &l1, V2 &l2) {   // line_
 inline Program build_miller_lines() {
     Builder b;
     g_b = &b;
+    g_fp2_shallow = true;
     V2 qx = {{b.leaf(BUF_IN0, 0)}, {b.leaf(BUF_IN0, 1)}}, qy = {{b.leaf(BUF_IN0, 2)}, {b.leaf(BUF_IN0, 3)}};
     V px = {b.leaf(BUF_IN1, 0)}, py = {b.leaf(BUF_IN1, 1)};
     V npx = vneg(px);
@@ -553,6 +571,7 @@ inline Program build_miller_lines() {
         }
     }
     g_b = nullptr;
+    g_fp2_shallow = false;
     return compile(b);
 }
 
