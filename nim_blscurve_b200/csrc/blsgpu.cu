@@ -51,6 +51,7 @@ struct blsgpu_ctx {
     uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
     cudaEvent_t ev[2 * ST_COUNT + 3];                        // stage begin/end pairs + fork/join/G1-ready
     bool ev_valid[2 * ST_COUNT + 3];
+    cudaStream_t side2 = nullptr;                            // small batches: [r_i] pk_i beside both the hash and the signature work
     cudaStream_t side = nullptr;                             // the signature-side MSM runs beside the per-set stages
     bool use_side = true;
     float stage_ms[ST_COUNT];
@@ -110,6 +111,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2 * ST_COUNT + 3; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -176,6 +178,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
         ctx->ev_valid[i] = true;
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
     if (getenv("BLSGPU_SIDE_STREAM")) ctx->use_side = atoi(getenv("BLSGPU_SIDE_STREAM")) != 0;
     return ctx;
 }
@@ -441,10 +444,12 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     // second stream instead of queueing behind the hash kernel.  Large batches fill the machine either way.
     const bool g1_aside = ctx->use_side && n < 2048;
     if (g1_aside) {
-        BEGIN(ST_G1MUL, g);
-        k_g1_mul<<<nblk(n), 128, 0, g>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
-        END(ST_G1MUL, g);
-        CK(cudaEventRecord(ctx->ev[EV_G1], g));
+        cudaStream_t g1s = ctx->side2;
+        CK(cudaStreamWaitEvent(g1s, ctx->ev[EV_FORK], 0));
+        BEGIN(ST_G1MUL, g1s);
+        k_g1_mul<<<nblk(n), 128, 0, g1s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
+        END(ST_G1MUL, g1s);
+        CK(cudaEventRecord(ctx->ev[EV_G1], g1s));
     }
     // Small-batch route: the serial stretches of a set (cofactor clearing, [r_i] sig_i) run as per-set dataflow
     // programs, one warp per set (fpprog.hpp build_g2_clear_cofactor / build_g2_mul64)
