@@ -175,7 +175,8 @@ const char *blsgpu_stage_name(int stage);
 int blsgpu_last_launches(const blsgpu_ctx *ctx);
 
 /* Test/diagnostic entry points */
-/* Fp unit ops on the device: op 0=mul 1=add 2=sub 3=sqr 4=inverse; a,b,out: n x 48 bytes (Montgomery). */
+/* Fp unit ops on the device: op 0=mul 1=add 2=sub 3=sqr 4=inverse (Fermat) 6=inverse (binary Euclid); a,b,out: n x 48
+ * bytes (Montgomery). */
 int blsgpu_test_fp(blsgpu_ctx *ctx, int op, const void *a, const void *b, size_t n, void *out);
 /* The message hash of the small-batch route (two-lane map kernel, then the cofactor-clearing dataflow program):
  * n <= 4096 sets in (host, 320 B each); out_in / out_out (nullable): n x 6 field elements (48 B each, Montgomery) =

@@ -804,6 +804,7 @@ __global__ void k_test_fp(int op, const fp *a, const fp *b, size_t n, fp *out) {
         case 1: fp_add(r, x, y); break;
         case 2: fp_sub(r, x, y); break;
         case 3: fp_sqr(r, x); break;
+        case 6: fp_inv_vartime(r, x); break;
         default: fp_inv(r, x); break;
     }
     out[i] = r;

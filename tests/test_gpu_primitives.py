@@ -34,6 +34,12 @@ def test_fp_ptx_vs_blst(cache, br):
         for i in range(0, n, 97):
             ref = br.fp_op(name, ab[48 * i:48 * i + 48], bb[48 * i:48 * i + 48])
             assert got[48 * i:48 * i + 48] == ref
+    # the binary-Euclid inversion of the single-thread tails
+    out = (C.c_uint8 * (48 * n))()
+    assert bg.lib().blsgpu_test_fp(cache.handle, 6, ab, None, n, out) == 0
+    got = bytes(out)
+    for i in range(0, n, 13):
+        assert got[48 * i:48 * i + 48] == br.fp_op("inv", ab[48 * i:48 * i + 48]), ("inv_vartime", i)
     out = (C.c_uint8 * (48 * 64))()
     assert bg.lib().blsgpu_test_fp(cache.handle, 4, ab[48 * 64:48 * 128], None, 64, out) == 0
     for i in range(64):
