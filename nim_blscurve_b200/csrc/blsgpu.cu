@@ -280,8 +280,11 @@ static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp 
 
 // one warp per instance: n instances of a per-set program on stream st, strides in field elements
 static int launch_prog_many(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, cudaStream_t st, size_t n, const fp *in0, size_t s_in0,
-                            const fp *in1, size_t s_in1, fp *out0, size_t s_out) {
-    k_fp_program<<<(unsigned)n, 32, (size_t)p.nslots * sizeof(fp), st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
+                            const fp *in1, size_t s_in1, fp *out0, size_t s_out, bool stream_outputs = false) {
+    if (stream_outputs)
+        k_fp_program_stream<<<(unsigned)n, 32, (size_t)p.nslots * sizeof(fp), st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
+    else
+        k_fp_program<<<(unsigned)n, 32, (size_t)p.nslots * sizeof(fp), st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
     ctx->launches++;
     return 0;
 }
@@ -296,7 +299,7 @@ static size_t small_route_max() {
 }
 static size_t small_lines_max() {
     static const size_t v = getenv("BLSGPU_SMALL_LINES_MAX") ? (size_t)atoll(getenv("BLSGPU_SMALL_LINES_MAX")) : 2049;
-    return v > SMALL_ROUTE_CAP + 1 ? SMALL_ROUTE_CAP + 1 : v;
+    return v > 16385 ? 16385 : v;
 }
 #define SMALL_ROUTE_MAX SMALL_ROUTE_CAP   /* buffer strides */
 #define SMALL_FP_PER_SET (6 + 6 + 6 + 6 + 64)
@@ -374,7 +377,7 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
             if (rc) return rc;
             const size_t per = (size_t)ML_NLINES * 6;
             if (!ctx->d_small_lines) CK(cudaMalloc((void **)&ctx->d_small_lines, small_lines_max() * per * sizeof(fp)));
-            launch_prog_many(ctx, lp, s, t, (const fp *)ctx->d_Q, 4, (const fp *)ctx->d_P, 2, ctx->d_small_lines, per);
+            launch_prog_many(ctx, lp, s, t, (const fp *)ctx->d_Q, 4, (const fp *)ctx->d_P, 2, ctx->d_small_lines, per, true);
             k_lines_from_prog<<<nblk(t * ML_NLINES * ML_LINE_WORDS, 256), 256, 0, s>>>((const uint32_t *)ctx->d_small_lines, ctx->d_Q, ctx->d_P, t,
                                                                                       ctx->d_lines, stride);
             ctx->launches++;

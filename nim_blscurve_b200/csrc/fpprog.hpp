@@ -29,7 +29,7 @@ enum { CONST_FROB1 = 0, CONST_FROB2 = 10, CONST_FROB3 = 20, CONST_PSI_CX = 30, C
        CONST_COUNT = 36 };
 
 struct Node { uint8_t op; int32_t a, b; };
-struct IoRef { int32_t node, buf, idx; };
+struct IoRef { int32_t node, buf, idx; bool stream = false; };
 
 struct Builder {
     std::vector<Node> nodes;
@@ -48,7 +48,13 @@ struct Builder {
         nodes.push_back({(uint8_t)op, a, b});
         return (int)nodes.size() - 1;
     }
-    void output(int node, int buf, int idx) { outputs.push_back({node, buf, idx}); }
+    // stream: the value is written to OUT0 by a STORE operation in the round after it is computed and its slot is freed,
+    // instead of staying resident until the end of the program (programs with hundreds of outputs)
+    void output(int node, int buf, int idx, bool stream = false) {
+        IoRef r{node, buf, idx};
+        r.stream = stream && node != 0 && buf == BUF_OUT0 && nodes[node].op != OP_LEAF;
+        outputs.push_back(r);
+    }
 };
 
 static thread_local Builder *g_b = nullptr;
@@ -289,12 +295,23 @@ inline Program compile(const Builder &B, int slack = 40) {
         rounds.push_back(ops);
         round_is_mul.push_back(is_mul);
     }
+    // streamed outputs: a STORE lane in the first round after the producer that has a free lane (or a new last round)
+    std::vector<std::vector<std::pair<int, int>>> stores(rounds.size());      // per round: (node, OUT0 index)
+    for (const IoRef &o : B.outputs) {
+        if (!o.stream) continue;
+        size_t q = (size_t)round_of[o.node] + 1;
+        while (q < rounds.size() && rounds[q].size() + stores[q].size() >= (size_t)LANES) q++;
+        if (q >= rounds.size()) { rounds.push_back({}); round_is_mul.push_back(0); stores.push_back({}); q = rounds.size() - 1; }
+        stores[q].push_back({o.node, o.idx});
+    }
     // liveness: last round in which each value is read
     const int NR = (int)rounds.size();
     std::vector<int> last_use(N, -1);
-    for (int r = 0; r < NR; r++)
+    for (int r = 0; r < NR; r++) {
         for (int n : rounds[r]) { last_use[B.nodes[n].a] = r; last_use[B.nodes[n].b] = r; }
-    for (const IoRef &o : B.outputs) last_use[o.node] = NR + 1;
+        for (const auto &st : stores[r]) last_use[st.first] = std::max(last_use[st.first], r);
+    }
+    for (const IoRef &o : B.outputs) if (!o.stream) last_use[o.node] = NR + 1;
     last_use[0] = NR + 1;
     std::vector<int> slot(N, -1);
     slot[0] = 0;
@@ -319,15 +336,22 @@ inline Program compile(const Builder &B, int slack = 40) {
     // serialise
     std::vector<IoRef> ins;
     for (const IoRef &in : B.inputs) if (live[in.node]) ins.push_back(in);
-    P.words = {(uint32_t)NR, (uint32_t)P.nslots, (uint32_t)ins.size(), (uint32_t)B.outputs.size()};
+    std::vector<IoRef> outs;
+    for (const IoRef &o : B.outputs) if (!o.stream) outs.push_back(o);
+    P.words = {(uint32_t)NR, (uint32_t)P.nslots, (uint32_t)ins.size(), (uint32_t)outs.size()};
     for (const IoRef &in : ins) { P.words.push_back((uint32_t)slot[in.node]); P.words.push_back(((uint32_t)in.buf << 24) | (uint32_t)in.idx); }
-    for (const IoRef &o : B.outputs) { P.words.push_back((uint32_t)slot[o.node]); P.words.push_back(((uint32_t)o.buf << 24) | (uint32_t)o.idx); }
+    for (const IoRef &o : outs) { P.words.push_back((uint32_t)slot[o.node]); P.words.push_back(((uint32_t)o.buf << 24) | (uint32_t)o.idx); }
     for (int r = 0; r < NR; r++) {
+        const int nops = (int)rounds[r].size();
         for (int l = 0; l < LANES; l++) {
-            if (l < (int)rounds[r].size()) {
+            if (l < nops) {
                 int n = rounds[r][l];
                 P.words.push_back(enc(B.nodes[n].op, slot[n], slot[B.nodes[n].a], slot[B.nodes[n].b]));
                 P.nops++;
+            } else if (l - nops < (int)stores[r].size()) {
+                // STORE: opcode 0 with a non-zero word; OUT0 index split over the d and b fields (20 bits)
+                const std::pair<int, int> &st = stores[r][l - nops];
+                P.words.push_back(enc(OP_NOP, (st.second >> 10) & 1023, slot[st.first], st.second & 1023));
             } else {
                 P.words.push_back(0u);
             }
@@ -556,8 +580,8 @@ inline Program build_miller_lines() {
         V2 c[3] = {l0, l1, l2};
         for (int k = 0; k < 3; k++) {
             // outputs must be computed nodes or leaves with their own slot; "+ 0" folds away, so route through the table
-            b.output(c[k].c0.id, BUF_OUT0, 6 * s + 2 * k);
-            b.output(c[k].c1.id, BUF_OUT0, 6 * s + 2 * k + 1);
+            b.output(c[k].c0.id, BUF_OUT0, 6 * s + 2 * k, true);
+            b.output(c[k].c1.id, BUF_OUT0, 6 * s + 2 * k + 1, true);
         }
         s++;
     };
@@ -572,7 +596,9 @@ inline Program build_miller_lines() {
     }
     g_b = nullptr;
     g_fp2_shallow = false;
-    return compile(b);
+    // no deferral of off-critical-path operations: the line scalings are ready early, few, and their streamed results
+    // free their slots at once — deferring them to the end is what would keep hundreds of values alive
+    return compile(b, 1 << 28);
 }
 
 }  // namespace fpprog

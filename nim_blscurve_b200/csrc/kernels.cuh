@@ -574,8 +574,11 @@ __global__ void k_copy_flag(const int *src, int *dst) {
 // One warp per block; block b runs the program on instance b: in0 + b * s_in0, in1 + b * s_in1, out0 + b * s_out
 // (strides in field elements; the per-batch tails launch one block with zero strides, the small-batch route one block
 // per signature set).
-__global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst, fp *out0,
-                                                   size_t s_in0, size_t s_in1, size_t s_out) {
+// STREAM: the program contains STORE operations (streamed outputs, fpprog.hpp); a separate instantiation because the
+// round loop is latency-bound to the instruction — the extra branch costs the programs that do not need it 10 %.
+template <bool STREAM>
+__device__ __forceinline__ void fp_program_body(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst, fp *out0,
+                                                size_t s_in0, size_t s_in1, size_t s_out) {
     extern __shared__ uint4 sm4[];
     fp *slots = (fp *)sm4;
     const int lane = threadIdx.x;
@@ -600,7 +603,18 @@ __global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const f
         for (int k = 0; k < 4; k++) {
             const uint32_t w = wq[k];
             wq[k] = r + k + 4 < nr ? rp[32 * (r + k + 4)] : 0u;
-            if (w) {
+            if (STREAM) {
+                const uint32_t opc = w >> 30;
+                if (opc) {
+                    fp x = slots[(w >> 10) & 1023], y = slots[w & 1023], t;
+                    if (opc == 1) fp_mul(t, x, y);
+                    else if (opc == 2) fp_add(t, x, y);
+                    else fp_sub(t, x, y);
+                    slots[(w >> 20) & 1023] = t;
+                } else if (w) {                           // STORE: a streamed output leaves its slot now
+                    out0[(((w >> 20) & 1023) << 10) | (w & 1023)] = slots[(w >> 10) & 1023];
+                }
+            } else if (w) {
                 fp x = slots[(w >> 10) & 1023], y = slots[w & 1023], t;
                 const uint32_t opc = w >> 30;
                 if (opc == 1) fp_mul(t, x, y);
@@ -613,6 +627,14 @@ __global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const f
     }
     const uint32_t *op = prog + 4 + 2 * nin;
     for (uint32_t e = lane; e < nout; e += 32) out0[op[2 * e + 1] & 0xffffffu] = slots[op[2 * e]];
+}
+__global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst, fp *out0,
+                                                   size_t s_in0, size_t s_in1, size_t s_out) {
+    fp_program_body<false>(prog, in0, in1, cst, out0, s_in0, s_in1, s_out);
+}
+__global__ void __launch_bounds__(32) k_fp_program_stream(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst,
+                                                          fp *out0, size_t s_in0, size_t s_in1, size_t s_out) {
+    fp_program_body<true>(prog, in0, in1, cst, out0, s_in0, s_in1, s_out);
 }
 
 // the Fp inversion lifted out of the final-exponentiation program (fpprog.hpp INV_EXTERNAL): one thread, binary Euclid

@@ -52,7 +52,9 @@ static inline void msm_free(msm_state &m) {
     m.bytes = 0;
 }
 
+#ifndef MSM_BIG
 #define MSM_BIG 32
+#endif
 
 // signed digit of window w (width c) of the nbits-bit little-endian scalar at sc (sb bytes)
 __device__ __forceinline__ int msm_digit(const uint8_t *sc, int sb, int nbits, int c, int w, int &carry) {

@@ -114,10 +114,11 @@ static void run_program(const std::vector<uint32_t> &w, const fp *in0, const fp 
         for (int l = 0; l < 32; l++) {              // all lanes read before any lane writes (stricter than the device)
             uint32_t x = rp[l];
             if (!x) continue;
+            if ((x >> 30) == 0) { out0[(((x >> 20) & 1023) << 10) | (x & 1023)] = slots[(x >> 10) & 1023]; continue; }   // STORE
             const fp &a = slots[(x >> 10) & 1023], &b = slots[x & 1023];
             if ((x >> 30) == 1) fp_mul(res[l], a, b); else if ((x >> 30) == 2) fp_add(res[l], a, b); else fp_sub(res[l], a, b);
         }
-        for (int l = 0; l < 32; l++) if (rp[l]) slots[(rp[l] >> 20) & 1023] = res[l];
+        for (int l = 0; l < 32; l++) if (rp[l] >> 30) slots[(rp[l] >> 20) & 1023] = res[l];
     }
     const uint32_t *op = w.data() + 4 + 2 * nin;
     for (uint32_t e = 0; e < nout; e++) out0[op[2 * e + 1] & 0xffffffu] = slots[op[2 * e]];
