@@ -467,6 +467,23 @@ inline Program build_msm_horner_g1(int nwin, int c) {
     g_b = nullptr;
     return compile(b);
 }
+// the same over Fp2 for a G2 MSM (the signature sum of a batch): IN0 = nwin x 6 fp, OUT0[0..5]
+inline PT<V2> load_g2(int buf, int base);
+inline void store_g2(PT<V2> p, int buf, int base);
+inline Program build_msm_horner_g2(int nwin, int c) {
+    Builder b;
+    g_b = &b;
+    g_fp2_shallow = true;
+    PT<V2> acc = load_g2(BUF_IN0, 6 * (nwin - 1));
+    for (int w = nwin - 2; w >= 0; w--) {
+        for (int k = 0; k < c; k++) acc = rcb_dbl(acc);
+        acc = rcb_add(acc, load_g2(BUF_IN0, 6 * w));
+    }
+    store_g2(acc, BUF_OUT0, 0);
+    g_b = nullptr;
+    g_fp2_shallow = false;
+    return compile(b);
+}
 
 // ---- per-set G2 programs of the small-batch route (one warp per signature set, k_fp_program_many) ----------------
 inline PT<V2> load_g2(int buf, int base) {

@@ -36,7 +36,7 @@ struct msm_state {
     // window-group pipelining: the latency-bound tail of a group (combine, segment, tree, Horner) runs on this
     // higher-priority stream underneath the bucket accumulation of the next group
     struct horner_prog { uint32_t *d = nullptr; int nslots = 0; };
-    std::map<int, horner_prog> horner;      // G1 window-Horner dataflow programs (fpprog.hpp), keyed by nwin * 64 + c
+    std::map<int, horner_prog> horner;      // window-Horner dataflow programs (fpprog.hpp), keyed by (nwin * 64 + c) * 2 + is_g2
     cudaStream_t tail = nullptr;
     cudaEvent_t ev_group[8] = {}, ev_done = nullptr;
     bool ev_ok = false;
@@ -380,6 +380,33 @@ __global__ void k_msm_horner_finish(const fp *hom, g1_jac *out_jac, g1_aff *out_
     }
 }
 
+// the G2 forms (window sums of the signature-side MSM; Jacobian result only)
+__global__ void k_msm_horner_prep_g2(const g2_jac *W, size_t stride, int nwin, fp *hom) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwin) return;
+    g2_jac p = W[(size_t)w * stride];
+    g2_jac_to_hom(hom + 6 * w, p);
+}
+__global__ void k_msm_horner_finish_g2(const fp *hom, g2_jac *out_jac, g2_aff *out_aff) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    fp2 X, Y, Z;
+    X.c0 = hom[0]; X.c1 = hom[1]; Y.c0 = hom[2]; Y.c1 = hom[3]; Z.c0 = hom[4]; Z.c1 = hom[5];
+    if (out_jac) {
+        g2_jac j;
+        if (fp2_is_zero(Z)) pt_set_inf(j);
+        else { fp2 z2; fp2_mul(j.x, X, Z); fp2_sqr(z2, Z); fp2_mul(j.y, Y, z2); j.z = Z; }
+        *out_jac = j;
+    }
+    if (out_aff) {
+        g2_aff a;
+        fp2 zi;
+        fp2_inv_vartime(zi, Z);
+        fp2_mul(a.x, X, zi);
+        fp2_mul(a.y, Y, zi);
+        *out_aff = a;
+    }
+}
+
 // synthetic MSM inputs (benchmark only): P_i = [k_i]G1 with a 96-bit k_i, 255-bit coefficients
 // (shape of benchmarks/bls12381_msm_g1.nim:22-44)
 __global__ void BLS_LB k_msm_make_inputs(uint64_t seed, size_t n, g1_aff *points, uint8_t *scalars) {
@@ -488,7 +515,7 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
     size_t o_bigcount = o_big + al(nb * 4);
     size_t o_carry = o_bigcount + 256;
     size_t o_hom = o_carry + al(sizeof(J));
-    size_t o_entries = o_hom + al((size_t)(3 * nwin + 3) * 48);
+    size_t o_entries = o_hom + al((size_t)(6 * nwin + 6) * 48);
     size_t o_partials = o_entries + al(emax * 4);
     size_t o_buckets = o_partials + al(pmax * sizeof(J));
     size_t o_segs = o_buckets + al(nb * sizeof(J));
@@ -552,27 +579,32 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
             m = half;
         }
         bool programmed = false;
-        if constexpr (std::is_same<F, fp>::value) {
+        {
             static const bool prog_env = !(getenv("BLSGPU_MSM_HORNER_PROG") && atoi(getenv("BLSGPU_MSM_HORNER_PROG")) == 0);
+            constexpr bool is_g1 = std::is_same<F, fp>::value;
+            constexpr int per = is_g1 ? 3 : 6;               // field elements per homogeneous point
             if (G == 1 && nwin <= 128 && prog_env) {
                 msm_state::horner_prog hp;
-                auto it = st.horner.find(nwin * 64 + c);
+                const int key = (nwin * 64 + c) * 2 + (is_g1 ? 0 : 1);
+                auto it = st.horner.find(key);
                 if (it != st.horner.end()) hp = it->second;
                 else {
-                    fpprog::Program P = fpprog::build_msm_horner_g1(nwin, c);
+                    fpprog::Program P = is_g1 ? fpprog::build_msm_horner_g1(nwin, c) : fpprog::build_msm_horner_g2(nwin, c);
                     if (P.ok && (size_t)P.nslots * sizeof(fp) <= 48 * 1024) {
                         MCK(cudaMalloc((void **)&hp.d, P.words.size() * 4));
                         MCK(cudaMemcpyAsync(hp.d, P.words.data(), P.words.size() * 4, cudaMemcpyHostToDevice, s));
                         MCK(cudaStreamSynchronize(s));       // first use of this shape only: the host vector goes away
                         hp.nslots = P.nslots;
                     }
-                    st.horner[nwin * 64 + c] = hp;
+                    st.horner[key] = hp;
                 }
                 if (hp.d) {
                     fp *hom = (fp *)(st.buf + o_hom);
-                    k_msm_horner_prep<<<1, 128, 0, ts>>>(sg, nseg, nwin, hom);
-                    k_fp_program<<<1, 32, (size_t)hp.nslots * sizeof(fp), ts>>>(hp.d, hom, nullptr, nullptr, hom + 3 * nwin, 0, 0, 0);
-                    k_msm_horner_finish<<<1, 32, 0, ts>>>(hom + 3 * nwin, d_out_jac, d_out_aff);
+                    if constexpr (is_g1) k_msm_horner_prep<<<1, 128, 0, ts>>>(sg, nseg, nwin, hom);
+                    else k_msm_horner_prep_g2<<<1, 128, 0, ts>>>(sg, nseg, nwin, hom);
+                    k_fp_program<<<1, 32, (size_t)hp.nslots * sizeof(fp), ts>>>(hp.d, hom, nullptr, nullptr, hom + per * nwin, 0, 0, 0);
+                    if constexpr (is_g1) k_msm_horner_finish<<<1, 32, 0, ts>>>(hom + per * nwin, d_out_jac, d_out_aff);
+                    else k_msm_horner_finish_g2<<<1, 32, 0, ts>>>(hom + per * nwin, d_out_jac, d_out_aff);
                     nl += 3;
                     programmed = true;
                 }

@@ -206,6 +206,13 @@ int hs_prog_miller_lines(const g2_aff *Q, const g1_aff *P, fp *out_prog, uint32_
     stats[0] = Pg.nrounds; stats[1] = Pg.nmul_rounds; stats[2] = Pg.nslots; stats[3] = Pg.nops;
     return 1;
 }
+int hs_prog_msm_horner_g2(const fp *hom, int nwin, int c, fp *out6, int *stats) {
+    fpprog::Program P = fpprog::build_msm_horner_g2(nwin, c);
+    if (!P.ok) return 0;
+    run_program(P.words, hom, nullptr, nullptr, out6);
+    stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
+    return 1;
+}
 int hs_pubkey_from_bytes(const uint8_t *in, int len, int group_check, g1_aff *out) { return pubkey_from_bytes(*out, in, len, group_check != 0); }
 int hs_signature_from_bytes(const uint8_t *in, int len, int group_check, g2_aff *out) { return signature_from_bytes(*out, in, len, group_check != 0); }
 void hs_g1_compress(const g1_aff *p, uint8_t *out) { g1_compress(out, *p); }

@@ -286,6 +286,25 @@ def test_g2_programs(hs):
     assert stats[2] <= 1024, list(stats)
 
 
+def test_msm_horner_program_g2(hs):
+    """build_msm_horner_g2 (window Horner of the signature-side MSM) == sum_w [2^(c w)] W_w by pyref, with an infinite
+    window and the 64-bit shape the batch verifier uses (5 windows of 13 bits)."""
+    rng = random.Random(55)
+    stats = (C.c_int * 4)()
+    g = pr.G2_GEN
+    for nwin, c, holes in ((5, 13, ()), (3, 4, (1,)), (1, 7, ())):
+        ws = [None if w in holes else pr.g2_mul(g, rng.randrange(1, 1 << 64)) for w in range(nwin)]
+        exp = None
+        for w in range(nwin - 1, -1, -1):
+            if w != nwin - 1 and exp is not None:
+                exp = pr.g2_mul(exp, 1 << c)
+            exp = pr.g2_add(exp, ws[w])
+        inp = b"".join(_g2_hom_bytes(pt, rng) for pt in ws)
+        r = out(6 * 48)
+        assert hs.hs_prog_msm_horner_g2(buf(inp), nwin, c, r, stats) == 1
+        assert _g2_from_hom(bytes(r)) == exp, (nwin, c)
+
+
 def test_miller_lines_program(hs):
     """fpprog.hpp build_miller_lines == pairing.cuh miller_lines, word for word (every Fp value is canonical, so equal
     formulas give equal bits): 68 line triples of a pair, for several (Q, P)."""
