@@ -59,7 +59,7 @@ struct blsgpu_ctx {
     msm_state msm;
     // warp-cooperative tail programs (fpprog.hpp), compiled on first use and kept on the device
     struct dev_prog { uint32_t *d = nullptr; int nslots = 0, nrounds = 0; };
-    std::map<int, dev_prog> combine_progs, final_progs, norm_progs, set_progs;   // keyed by segment count / partial count
+    std::map<int, dev_prog> combine_progs, final_progs, norm_progs, set_progs, prod_progs;   // keyed by segment count / partial count
     fp *d_small_lines = nullptr;                             // 68 x 6 field elements per pair (small-batch route)
     fp *d_small = nullptr;                                   // per-set program inputs/outputs of the small-batch route
     fp *d_norm = nullptr;                                    // [0] Fp norm taken out of the final exponentiation, [1] its inverse
@@ -106,6 +106,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     for (auto &kv : ctx->final_progs) cudaFree(kv.second.d);
     for (auto &kv : ctx->norm_progs) cudaFree(kv.second.d);
     for (auto &kv : ctx->set_progs) cudaFree(kv.second.d);
+    for (auto &kv : ctx->prod_progs) cudaFree(kv.second.d);
     cudaFree(ctx->d_norm); cudaFree(ctx->d_small); cudaFree(ctx->d_small_lines); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -239,9 +240,9 @@ enum { SETPROG_COFACTOR = 0, SETPROG_G2MUL64 = 1, SETPROG_LINES = 2 };
 
 // Compile (once) and fetch a tail program; kind 0 = combine over `key` segments, 1 = final exponentiation of `key`
 // partials with the Fp inversion supplied in IN1, 2 = the norm that inversion applies to (fpprog.hpp build_final),
-// 3 = per-set G2 program `key` (SETPROG_*)
+// 3 = per-set G2 program `key` (SETPROG_*), 4 = product tree over `key` Fp12 values
 static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &out) {
-    std::map<int, blsgpu_ctx::dev_prog> &cache = kind == 0 ? ctx->combine_progs : (kind == 1 ? ctx->final_progs : (kind == 2 ? ctx->norm_progs : ctx->set_progs));
+    std::map<int, blsgpu_ctx::dev_prog> &cache = kind == 0 ? ctx->combine_progs : (kind == 1 ? ctx->final_progs : (kind == 2 ? ctx->norm_progs : (kind == 3 ? ctx->set_progs : ctx->prod_progs)));
     auto it = cache.find(key);
     if (it != cache.end()) { out = it->second; return 0; }
     fpprog::Program P;
@@ -249,6 +250,8 @@ static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &ou
         int len[64];
         for (int j = 0; j < key; j++) len[j] = ml_seg_hi(j, key) - ml_seg_lo(j, key) + 1;
         P = fpprog::build_combine(key, len);
+    } else if (kind == 4) {                              // product of `key` Fp12 values (GT product of a small batch)
+        P = fpprog::build_fp12_product(key);
     } else if (kind == 3) {                              // per-set programs of the small-batch route
         P = key == SETPROG_COFACTOR ? fpprog::build_g2_clear_cofactor() : (key == SETPROG_G2MUL64 ? fpprog::build_g2_mul64() : fpprog::build_miller_lines());
     } else {
@@ -310,7 +313,8 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
     if (team && np <= 8192) {
         // Latency regime (the machine is not full).  Measured on B200 (tools/gpu_small_sweep.sh): a team spends ~7.5 us
         // per (squaring or line) step while all teams are resident (~12k of them), the product over groups is one
-        // block-wide tree (0.59 ms) up to 128 groups and two launches (1.16 ms) beyond (0.084 ms per tree level), the segment Horner program costs
+        // block-wide tree (0.59 ms) up to 128 groups and two launches (1.16 ms) beyond (0.084 ms per tree level); up to 64 groups it is a pair of product-tree programs,
+        // one warp per row (0.04-0.08 ms), the segment Horner program costs
         // 0.22 ms + 7.4 us per segment.
         double best = 0.0;
         G = 1; nseg = 32;
@@ -319,10 +323,11 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
                 const size_t ngroups = (np + g - 1) / g;
                 if (ngroups * ns > 32768) continue;             // d_F holds at least 40 000 (group, segment) products
                 const double waves = (double)((ngroups * ns + 11999) / 12000);
-                const double acc = waves * (double)((63 + ns - 1) / ns) * (1 + g) * 7.5e-3;
+                const double acc = waves * (double)((63 + ns - 1) / ns) * (1 + g) * (g <= 16 ? 7.5e-3 : 9.5e-3);
                 int depth = 0;
                 while (((size_t)1 << depth) < ngroups) depth++;
-                const double cost = acc + (ngroups <= 128 ? 0.084 * depth : 1.16) + 0.22 + 7.4e-3 * ns;
+                const double gtp = ngroups <= 8 ? 0.04 : (ngroups <= 64 ? 0.08 : (ngroups <= 128 ? 0.084 * depth : 1.16));
+                const double cost = acc + gtp + 0.22 + 7.4e-3 * ns;
                 if (best == 0.0 || cost < best) { best = cost; G = g; nseg = ns; }
             }
     } else if (team) {                             // ~32k teams: 6 lanes each, squarings are cheap to share widely
@@ -359,6 +364,11 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
         size_t ngroups = (t + G - 1) / G;
         ncols += team ? ngroups : (ngroups + BLS_ACC_BS - 1) / BLS_ACC_BS;
     }
+    // small batches: the GT product of each segment row runs as product-tree programs over groups of 8 columns, so
+    // the rows of d_F are padded to a multiple of 8 with ones
+    static const int gt_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 15;   // bit 3: GT product
+    const bool gt_prog = (gt_env & 8) && team && np <= ctx->lines_cap && ncols <= 64 && !ctx->serial_tail;
+    const size_t row_stride = gt_prog && ncols > 8 ? ((ncols + 7) & ~(size_t)7) : ncols;
     const size_t ncols2 = (ncols + BLS_ACC_BS - 1) / BLS_ACC_BS;
     if ((size_t)nseg * ncols > ctx->f_cap || (size_t)nseg * ncols2 > ctx->f2_cap)
         return fail(ctx, BLSGPU_ERR_CAPACITY, "segment product buffer too small");
@@ -368,7 +378,7 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
     for (size_t off = 0; off < np; off += ctx->lines_cap) {
         size_t t = np - off < ctx->lines_cap ? np - off : ctx->lines_cap;
         size_t stride = ctx->lines_cap;
-        static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 7;   // bit 2: lines
+        static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 15;   // bit 2: lines
         if ((small_env & 4) && single && np <= small_lines_max() && !ctx->serial_tail) {
             // one warp per pair runs the 68 line evaluations as a dataflow program (two multiplication levels per
             // tangent instead of ~20 dependent products), then a scatter into the accumulation's layout
@@ -388,7 +398,7 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
         size_t ngroups = (t + G - 1) / G;
         if (team) {
             dim3 grid(nblk(ngroups, ACC_TPB), nseg);
-            k_miller_acc_team<<<grid, ACC_BS, 0, s>>>(ctx->d_lines, stride, t, ngroups, G, nseg, ctx->d_F, ncols, col);
+            k_miller_acc_team<<<grid, ACC_BS, 0, s>>>(ctx->d_lines, stride, t, ngroups, G, nseg, ctx->d_F, row_stride, col);
             col += ngroups;
         } else {
             dim3 grid(nblk(ngroups, BLS_ACC_BS), nseg);
@@ -400,7 +410,23 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
     if (!single) { END(ST_LINES, s); BEGIN(ST_ACC, s); }    // multi-tile: lines+acc are reported together under miller_lines
     END(ST_ACC, s);
     BEGIN(ST_GTPROD, s);
-    if (ncols > BLS_ACC_BS) {
+    if (gt_prog) {
+        blsgpu_ctx::dev_prog p8, pm;
+        if (ncols <= 8) {
+            rc = get_prog(ctx, 4, (int)ncols, pm);
+            if (rc) return rc;
+            launch_prog_many(ctx, pm, s, (size_t)nseg, (const fp *)ctx->d_F, 12 * ncols, nullptr, 0, (fp *)ctx->d_seg, 12);
+        } else {
+            const int m = (int)(row_stride / 8);
+            rc = get_prog(ctx, 4, 8, p8);
+            if (!rc) rc = get_prog(ctx, 4, m, pm);
+            if (rc) return rc;
+            k_fp12_pad_one<<<nseg, 32, 0, s>>>(ctx->d_F, row_stride, ncols);
+            launch_prog_many(ctx, p8, s, (size_t)nseg * m, (const fp *)ctx->d_F, 96, nullptr, 0, (fp *)ctx->d_F2, 12);
+            launch_prog_many(ctx, pm, s, (size_t)nseg, (const fp *)ctx->d_F2, 12 * (size_t)m, nullptr, 0, (fp *)ctx->d_seg, 12);
+            ctx->launches++;
+        }
+    } else if (ncols > BLS_ACC_BS) {
         dim3 grid((unsigned)ncols2, nseg);
         k_fp12_rows_step<<<grid, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_F2, ncols2);
         k_fp12_rows<<<nseg, BLS_ACC_BS, 0, s>>>(ctx->d_F2, ncols2, ncols2, ctx->d_seg);
@@ -456,7 +482,7 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     }
     // Small-batch route: the serial stretches of a set (cofactor clearing, [r_i] sig_i) run as per-set dataflow
     // programs, one warp per set (fpprog.hpp build_g2_clear_cofactor / build_g2_mul64)
-    static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 7;   // bit 0 hash, bit 1 sig (bit 2: lines, run_miller)
+    static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 15;   // bit 0 hash, bit 1 sig (bit 2: lines, bit 3: GT product, run_miller)
     const bool small = small_env != 0 && n <= small_route_max() && !ctx->serial_tail;
     const bool small_hash = small && (small_env & 1), small_sig = small && (small_env & 2);
     blsgpu_ctx::dev_prog p_cof, p_mul;
@@ -794,7 +820,7 @@ static int verify_pairs_dev(blsgpu_ctx *ctx, const g1_aff *d_pks, size_t n, cons
     ctx->launches = 0;
     CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
     BEGIN(ST_HASH, s);
-    static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 7;
+    static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 15;
     if ((small_env & 1) && n <= small_route_max() && !ctx->serial_tail) {
         // small-batch route (see run_partial): two lanes per message, cofactor clearing as a per-message program
         blsgpu_ctx::dev_prog p_cof;

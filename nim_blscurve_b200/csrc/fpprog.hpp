@@ -401,6 +401,25 @@ inline Program build_final(int count, int inv_mode = INV_INLINE) {
     return compile(b);
 }
 
+// product of `count` Fp12 values (IN0: count x 12 fp) -> OUT0: 12 fp; balanced tree.  One warp per segment row of a small
+// batch (blsgpu_merge-style GT product, aggregate.c:410-458): 54 multiplications per node spread over the 32 lanes
+// instead of one thread per node.
+inline Program build_fp12_product(int count) {
+    Builder b;
+    g_b = &b;
+    std::vector<V12> v;
+    for (int i = 0; i < count; i++) v.push_back(load12(BUF_IN0, 12 * i));
+    while (v.size() > 1) {
+        std::vector<V12> w;
+        for (size_t i = 0; i + 1 < v.size(); i += 2) w.push_back(v[i] * v[i + 1]);
+        if (v.size() & 1) w.push_back(v.back());
+        v.swap(w);
+    }
+    store12(v[0], BUF_OUT0, 0);
+    g_b = nullptr;
+    return compile(b);
+}
+
 // ---- G1 in homogeneous projective coordinates, complete formulas --------------------------------------------------
 // Renes-Costello-Batina (2016) algorithms 7 and 9 for y^2 = x^3 + b with a = 0, b = 4 (b3 = 12).  E(Fp) has odd order
 // (cofactor (z-1)^2/3 and r are odd), so the formulas have no exceptional inputs: infinity is (0 : y : 0), P + P,

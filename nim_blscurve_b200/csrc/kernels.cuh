@@ -529,6 +529,15 @@ __global__ void __launch_bounds__(BLS_ACC_BS, BLS_ACC_BLOCKS) k_fp12_rows_step(c
     if (threadIdx.x == 0) out[(size_t)blockIdx.y * out_stride + blockIdx.x] = f;
 }
 
+// rows of F padded to `stride` columns: columns [ncols, stride) of row blockIdx.x become one (small-batch GT product)
+__global__ void k_fp12_pad_one(fp12 *F, size_t stride, size_t ncols) {
+    const size_t c = ncols + threadIdx.x;
+    if (c >= stride) return;
+    fp12 one;
+    fp12_set_one(one);
+    F[(size_t)blockIdx.x * stride + c] = one;
+}
+
 // one block per segment row: product of ncols values -> seg[j]
 __global__ void __launch_bounds__(BLS_ACC_BS, BLS_ACC_BLOCKS) k_fp12_rows(const fp12 *Fseg, size_t row_stride, size_t ncols,
                                                                           fp12 *seg) {

@@ -213,6 +213,13 @@ int hs_prog_msm_horner_g2(const fp *hom, int nwin, int c, fp *out6, int *stats) 
     stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
     return 1;
 }
+int hs_prog_fp12_product(const fp12 *in, int count, fp12 *out, int *stats) {
+    fpprog::Program P = fpprog::build_fp12_product(count);
+    if (!P.ok) return 0;
+    run_program(P.words, (const fp *)in, nullptr, nullptr, (fp *)out);
+    stats[0] = P.nrounds; stats[1] = P.nmul_rounds; stats[2] = P.nslots; stats[3] = P.nops;
+    return 1;
+}
 int hs_pubkey_from_bytes(const uint8_t *in, int len, int group_check, g1_aff *out) { return pubkey_from_bytes(*out, in, len, group_check != 0); }
 int hs_signature_from_bytes(const uint8_t *in, int len, int group_check, g2_aff *out) { return signature_from_bytes(*out, in, len, group_check != 0); }
 void hs_g1_compress(const g1_aff *p, uint8_t *out) { g1_compress(out, *p); }

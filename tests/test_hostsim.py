@@ -286,6 +286,21 @@ def test_g2_programs(hs):
     assert stats[2] <= 1024, list(stats)
 
 
+def test_fp12_product_program(hs):
+    """build_fp12_product (GT product of a segment row in small batches) == the product by pyref."""
+    rng = random.Random(66)
+    stats = (C.c_int * 4)()
+    for count in (1, 2, 3, 5, 8, 16):
+        vals = [tuple(tuple((rng.randrange(P), rng.randrange(P)) for _ in range(3)) for _ in range(2)) for _ in range(count)]
+        r = out(576)
+        assert hs.hs_prog_fp12_product(buf(b"".join(f12b(x) for x in vals)), count, r, stats) == 1
+        prod = vals[0]
+        for x in vals[1:]:
+            prod = pr.f12_mul(prod, x)
+        assert f12f(bytes(r)) == prod, count
+        assert stats[2] <= 1024, (count, list(stats))
+
+
 def test_msm_horner_program_g2(hs):
     """build_msm_horner_g2 (window Horner of the signature-side MSM) == sum_w [2^(c w)] W_w by pyref, with an infinite
     window and the 64-bit shape the batch verifier uses (5 windows of 13 bits)."""
