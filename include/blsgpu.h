@@ -107,6 +107,12 @@ int blsgpu_hash_to_g2(blsgpu_ctx *ctx, const uint8_t *msgs, size_t n, size_t msg
 int blsgpu_aggregate_g1(blsgpu_ctx *ctx, const void *points96, size_t n, uint8_t out96[96]);
 int blsgpu_aggregate_g2(blsgpu_ctx *ctx, const void *points192, size_t n, uint8_t out192[192]);
 
+/* subtractAll (blst_min_pubkey_sig_core.nim:197-209; replaces its blst_p{1,2}_from_affine / _add_or_double_affine /
+ * _cneg / _to_affine calls): dst <- dst - sum of the n affine points, in place.  n == 0 leaves dst untouched (:199-200).
+ * Returns 1, or a negative error code. */
+int blsgpu_subtract_g1(blsgpu_ctx *ctx, uint8_t dst96[96], const void *elems96, size_t n);
+int blsgpu_subtract_g2(blsgpu_ctx *ctx, uint8_t dst192[192], const void *elems192, size_t n);
+
 /* Segmented aggregateAll: segment k sums points[offsets[k] .. offsets[k+1]) (an empty segment yields infinity, the case
  * aggregateAll reports as false, blst_min_pubkey_sig_core.nim:183-184); out96 receives nseg affine points.  One launch for
  * all committees of a block (128 x 128 + 512 public keys). */

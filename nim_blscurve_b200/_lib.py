@@ -15,7 +15,7 @@ SYMBOLS = [
     "blsgpu_set_stream", "blsgpu_rlc_scalars", "blsgpu_batch_verify", "blsgpu_batch_verify_dev",
     "blsgpu_partial", "blsgpu_partial_dev", "blsgpu_finalize", "blsgpu_finalize_dev", "blsgpu_hash_to_g2", "blsgpu_aggregate_g1", "blsgpu_aggregate_g2",
     "blsgpu_msm_g1", "blsgpu_msm_g1_dev", "blsgpu_msm_g2", "blsgpu_msm_g2_dev", "blsgpu_combine", "blsgpu_last_stage_ms", "blsgpu_stage_name", "blsgpu_last_launches",
-    "blsgpu_aggregate_g1_segments", "blsgpu_aggregate_verify", "blsgpu_fast_aggregate_verify",
+    "blsgpu_subtract_g1", "blsgpu_subtract_g2", "blsgpu_aggregate_g1_segments", "blsgpu_aggregate_verify", "blsgpu_fast_aggregate_verify",
     "blsgpu_pubkeys_from_bytes", "blsgpu_signatures_from_bytes", "blsgpu_pubkeys_to_bytes", "blsgpu_signatures_to_bytes",
     "blsgpu_test_fp", "blsgpu_test_small_hash", "blsgpu_imad_peak", "blsgpu_fpmul_peak", "blsgpu_make_sets", "blsgpu_msm_make_inputs",
 ]
@@ -56,6 +56,8 @@ def lib():
     L.blsgpu_test_small_hash.argtypes = [vp, vp, sz, vp, vp]
     L.blsgpu_aggregate_g1.argtypes = [vp, vp, sz, vp]
     L.blsgpu_aggregate_g2.argtypes = [vp, vp, sz, vp]
+    L.blsgpu_subtract_g1.argtypes = [vp, vp, vp, sz]
+    L.blsgpu_subtract_g2.argtypes = [vp, vp, vp, sz]
     L.blsgpu_msm_g1.argtypes = [vp, vp, vp, sz, sz, vp]
     L.blsgpu_msm_g1_dev.argtypes = [vp, vp, vp, sz, sz, vp]
     L.blsgpu_msm_g2.argtypes = [vp, vp, vp, sz, sz, vp]

@@ -9,6 +9,7 @@ Names, argument meaning and error behaviour follow the reference:
   * batchVerify(tp, cache, input, secureRandomBytes)                   :420-495  (parallel iff
     tp.numThreads > 1 and len >= 3, :440, :468)
   * aggregateAll(elems) -> (ok, point)                                 blst_min_pubkey_sig_core.nim:179-195
+  * subtractAll(dst, elems) -> point                                   blst_min_pubkey_sig_core.nim:197-209
 The Taskpool argument stays in the signatures; it no longer fans work out to threads — its
 numThreads only selects the reference's RLC-scalar chunking so results are identical for a given tp.
 """
@@ -142,6 +143,21 @@ def aggregateAll(cache: BatchedBLSVerifierCache, elems: Sequence[bytes]):
     if rc < 0:
         raise BlsGpuError(f"aggregate failed ({rc}): {cache.last_error()}")
     return bool(rc), bytes(out)
+
+
+def subtractAll(cache: BatchedBLSVerifierCache, dst: bytes, elems: Sequence[bytes]) -> bytes:
+    """dst - sum(elems) for public keys (96 B) or signatures (192 B); an empty `elems` returns dst unchanged
+    (blst_min_pubkey_sig_core.nim:197-209; the Nim proc updates `dst` in place, this mirror returns the new value)."""
+    sz = len(dst)
+    assert sz in (96, 192) and all(len(e) == sz for e in elems)
+    if len(elems) == 0:
+        return bytes(dst)
+    out = (C.c_uint8 * sz).from_buffer_copy(dst)
+    fn = lib().blsgpu_subtract_g1 if sz == 96 else lib().blsgpu_subtract_g2
+    rc = fn(cache.handle, out, b"".join(elems), len(elems))
+    if rc != 1:
+        raise BlsGpuError(f"subtract failed ({rc}): {cache.last_error()}")
+    return bytes(out)
 
 
 def hashToG2(cache: BatchedBLSVerifierCache, msgs: bytes, msg_len: int, dst: bytes):

@@ -812,6 +812,53 @@ extern "C" int blsgpu_aggregate_g2(blsgpu_ctx *ctx, const void *points192, size_
     return 1;
 }
 
+// ---- subtractAll (blst_min_pubkey_sig_core.nim:197-209) ----
+// dst - sum(elems) computed as -((sum(elems)) + (-dst)): one tree over n + 1 points with the negated dst in the last
+// slot, one negation of the root, one inversion.  Affine output, hence bit-identical to the reference's
+// aggregate / cneg / aggregate(dst) / finish sequence whatever the order of the additions.
+template <class F> static int subtract_all(blsgpu_ctx *ctx, void *dst, const void *elems, size_t n,
+                                           void (*load)(const aff_t<F> *, size_t, jac_t<F> *, cudaStream_t),
+                                           void (*tree)(jac_t<F> *, size_t, size_t, cudaStream_t),
+                                           void (*to_affine)(const jac_t<F> *, aff_t<F> *, cudaStream_t)) {
+    if (!ctx || !dst) return BLSGPU_ERR_ARG;
+    if (n == 0) return 1;                                   // :199-200: dst untouched
+    if (!elems) return BLSGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    size_t m = n + 1;
+    int rc = ensure_misc(ctx, m * (sizeof(aff_t<F>) + sizeof(jac_t<F>)) + 256);
+    if (rc) return rc;
+    jac_t<F> *J = (jac_t<F> *)ctx->d_misc;
+    aff_t<F> *A = (aff_t<F> *)((uint8_t *)ctx->d_misc + m * sizeof(jac_t<F>));
+    CK(cudaMemcpyAsync(A, elems, n * sizeof(aff_t<F>), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(A + n, dst, sizeof(aff_t<F>), cudaMemcpyHostToDevice, s));
+    load(A, m, J, s);
+    k_pt_neg<F><<<1, 32, 0, s>>>(J + n);
+    for (size_t k = m; k > 1;) { size_t half = (k + 1) / 2; tree(J, k, half, s); k = half; }
+    k_pt_neg<F><<<1, 32, 0, s>>>(J);
+    to_affine(J, A, s);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, A, sizeof(aff_t<F>), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 1;
+}
+
+extern "C" int blsgpu_subtract_g1(blsgpu_ctx *ctx, uint8_t dst96[96], const void *elems96, size_t n) {
+    return subtract_all<fp>(
+        ctx, dst96, elems96, n,
+        [](const g1_aff *a, size_t m, g1_jac *j, cudaStream_t s) { k_g1_load<<<nblk(m), 128, 0, s>>>(a, m, j); },
+        [](g1_jac *j, size_t k, size_t half, cudaStream_t s) { k_g1_tree<<<nblk(half), 128, 0, s>>>(j, k, half); },
+        [](const g1_jac *j, g1_aff *a, cudaStream_t s) { k_g1_to_affine<<<1, 32, 0, s>>>(j, a); });
+}
+
+extern "C" int blsgpu_subtract_g2(blsgpu_ctx *ctx, uint8_t dst192[192], const void *elems192, size_t n) {
+    return subtract_all<fp2>(
+        ctx, dst192, elems192, n,
+        [](const g2_aff *a, size_t m, g2_jac *j, cudaStream_t s) { k_g2_load<<<nblk(m), 128, 0, s>>>(a, m, j); },
+        [](g2_jac *j, size_t k, size_t half, cudaStream_t s) { k_g2_tree<<<nblk(half), 128, 0, s>>>(j, k, half); },
+        [](const g2_jac *j, g2_aff *a, cudaStream_t s) { k_g2_to_affine<<<1, 32, 0, s>>>(j, a); });
+}
+
 // ---- aggregateVerify / fastAggregateVerify on the device ----
 // d_pks: n affine public keys on the device; messages/DST/signature are staged into d_misc by the callers below.
 static int verify_pairs_dev(blsgpu_ctx *ctx, const g1_aff *d_pks, size_t n, const uint8_t *d_msgs, const uint32_t *d_offs,

@@ -824,6 +824,14 @@ __global__ void k_g2_to_affine(const g2_jac *in, g2_aff *out) {
     *out = a;
 }
 
+// subtractAll (blst_min_pubkey_sig_core.nim:197-209): blst_p{1,2}_cneg of one Jacobian point in place.
+template <class F> __global__ void k_pt_neg(jac_t<F> *p) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    jac_t<F> a = *p, r;
+    pt_neg(r, a);
+    *p = r;
+}
+
 // ---- diagnostics ----
 __global__ void k_test_fp(int op, const fp *a, const fp *b, size_t n, fp *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -2,7 +2,7 @@
 #
 # Public names, parameter lists and results are those of the reference (file:line into nim-blscurve):
 #   SignatureSet :34, BatchedBLSVerifierCache :62, init :108/:115, batchVerifySerial :121/:162,
-#   batchVerifyParallel :296/:373/:399, batchVerify :420/:449/:475, aggregateAll (blst_min_pubkey_sig_core.nim:179).
+#   batchVerifyParallel :296/:373/:399, batchVerify :420/:449/:475, aggregateAll / subtractAll (blst_min_pubkey_sig_core.nim:179, :197).
 # `tp: Taskpool` stays in the signatures; it no longer fans work out — tp.numThreads only selects the reference's
 # RLC-scalar chunking, so verdicts (and GT values) are identical to the BLST path for the same tp.
 # NOT compiled in the build container (no Nim toolchain); see INTEGRATION.md.
@@ -98,6 +98,15 @@ func aggregateAll*(cache: var BatchedBLSVerifierCache, dst: var PublicKey, elems
 func aggregateAll*(cache: var BatchedBLSVerifierCache, dst: var Signature, elems: openArray[Signature]): bool =
   if elems.len == 0: return false
   blsgpu_aggregate_g2(cache.ctx, unsafeAddr elems[0], elems.len.csize_t, addr dst) == 1
+
+proc subtractAll*(cache: var BatchedBLSVerifierCache, dst: var PublicKey, elems: openArray[PublicKey]) =
+  ## dst <- dst - sum(elems)                                   # blst_min_pubkey_sig_core.nim:197-209
+  if elems.len == 0: return
+  doAssert blsgpu_subtract_g1(cache.ctx, addr dst, unsafeAddr elems[0], elems.len.csize_t) == 1, "blsgpu_subtract_g1 failed"
+
+proc subtractAll*(cache: var BatchedBLSVerifierCache, dst: var Signature, elems: openArray[Signature]) =
+  if elems.len == 0: return
+  doAssert blsgpu_subtract_g2(cache.ctx, addr dst, unsafeAddr elems[0], elems.len.csize_t) == 1, "blsgpu_subtract_g2 failed"
 
 # --- SURVEY §8f N3: bls_sig_min_pubkey.nim:108-258 on the device (proof-of-possession overloads stay as they are:
 # they call popVerify per key and then these) ---

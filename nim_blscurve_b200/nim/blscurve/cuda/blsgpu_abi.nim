@@ -35,6 +35,8 @@ proc blsgpu_hash_to_g2*(ctx: BlsGpuCtx, msgs: ptr byte, n, msgLen: csize_t, dst:
                         outCompressed, outAffine: ptr byte): cint
 proc blsgpu_aggregate_g1*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: pointer): cint
 proc blsgpu_aggregate_g2*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: pointer): cint
+proc blsgpu_subtract_g1*(ctx: BlsGpuCtx, dst: pointer, elems: pointer, n: csize_t): cint
+proc blsgpu_subtract_g2*(ctx: BlsGpuCtx, dst: pointer, elems: pointer, n: csize_t): cint
 proc blsgpu_msm_g1*(ctx: BlsGpuCtx, points, scalars: pointer, n, nbits: csize_t, dst: pointer): cint
 proc blsgpu_msm_g2*(ctx: BlsGpuCtx, points, scalars: pointer, n, nbits: csize_t, dst: pointer): cint
 proc blsgpu_aggregate_g1_segments*(ctx: BlsGpuCtx, points: pointer, offsets: ptr uint32, nseg: csize_t,

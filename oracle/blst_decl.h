@@ -42,6 +42,7 @@ void blst_p2_add_or_double(blst_p2 *out, const blst_p2 *a, const blst_p2 *b);
 void blst_p2_add_or_double_affine(blst_p2 *out, const blst_p2 *a, const blst_p2_affine *b);
 void blst_p2_mult(blst_p2 *out, const blst_p2 *p, const uint8_t *scalar, size_t nbits);
 void blst_p2_cneg(blst_p2 *p, bool cbit);
+void blst_p1_cneg(blst_p1 *p, bool cbit);
 void blst_p2_affine_compress(uint8_t out[96], const blst_p2_affine *in);               /* blst.h:314 */
 void blst_p1_affine_compress(uint8_t out[48], const blst_p1_affine *in);               /* blst.h:310 */
 void blst_p1_affine_serialize(uint8_t out[96], const blst_p1_affine *in);

@@ -148,6 +148,16 @@ def aggregate_g2(points192):
     return bool(ok), bytes(out)
 
 
+def subtract_all(dst, points):
+    """subtractAll (blst_min_pubkey_sig_core.nim:197-209): dst - sum(points); 96-byte (G1) or 192-byte (G2) affine points."""
+    sz = len(dst)
+    assert sz in (96, 192) and len(points) % sz == 0
+    n = len(points) // sz
+    out = (C.c_uint8 * sz).from_buffer_copy(dst)
+    (ref.ref_subtract_g1 if sz == 96 else ref.ref_subtract_g2)(out, _buf(points) if n else None, C.c_size_t(n))
+    return bytes(out)
+
+
 def fast_aggregate_set(start_seed, nkeys, hashed32, threads=0):
     """Committee of nkeys signers on one message: returns (member pubkeys nkeys*96, aggregate set 320 B)."""
     pks, out = _out(96 * nkeys), _out(320)

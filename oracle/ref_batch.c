@@ -321,6 +321,25 @@ int ref_aggregate_g2(const uint8_t *pts, size_t n, uint8_t out[192]) {
     return 1;
 }
 
+/* ---------------- subtractAll (blst_min_pubkey_sig_core.nim:197-209) ---------------- */
+void ref_subtract_g1(uint8_t dst[96], const uint8_t *pts, size_t n) {
+    if (n == 0) return;                                                                 /* :199-200 */
+    blst_p1 acc; blst_p1_from_affine(&acc, (const blst_p1_affine *)pts);                /* :202 */
+    for (size_t i = 1; i < n; i++) blst_p1_add_or_double_affine(&acc, &acc, (const blst_p1_affine *)(pts + 96 * i));
+    blst_p1_cneg(&acc, 1);                                                              /* :204-207 */
+    blst_p1_add_or_double_affine(&acc, &acc, (const blst_p1_affine *)dst);              /* :208 */
+    blst_p1_to_affine((blst_p1_affine *)dst, &acc);                                     /* :209 */
+}
+
+void ref_subtract_g2(uint8_t dst[192], const uint8_t *pts, size_t n) {
+    if (n == 0) return;
+    blst_p2 acc; blst_p2_from_affine(&acc, (const blst_p2_affine *)pts);
+    for (size_t i = 1; i < n; i++) blst_p2_add_or_double_affine(&acc, &acc, (const blst_p2_affine *)(pts + 192 * i));
+    blst_p2_cneg(&acc, 1);
+    blst_p2_add_or_double_affine(&acc, &acc, (const blst_p2_affine *)dst);
+    blst_p2_to_affine((blst_p2_affine *)dst, &acc);
+}
+
 void ref_g2_neg(const uint8_t in[192], uint8_t out[192]) {
     blst_p2 p; blst_p2_from_affine(&p, (const blst_p2_affine *)in);
     blst_p2_cneg(&p, 1);

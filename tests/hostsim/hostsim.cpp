@@ -12,6 +12,23 @@
 #include "../../nim_blscurve_b200/csrc/fpprog.hpp"
 using namespace bls;
 
+// subtractAll as blsgpu.cu: subtract_all arranges it: pairwise tree over (elems..., -dst), negated root, to affine
+template <class F> static void hs_subtract(aff_t<F> *dst, const aff_t<F> *p, size_t n) {
+    size_t m = n + 1;
+    jac_t<F> *J = new jac_t<F>[m];
+    for (size_t i = 0; i < n; i++) pt_from_affine(J[i], p[i]);
+    pt_from_affine(J[n], *dst);
+    pt_neg(J[n], J[n]);
+    for (size_t k = m; k > 1;) {
+        size_t half = (k + 1) / 2;
+        for (size_t i = 0; i + half < k; i++) pt_add(J[i], J[i], J[i + half]);
+        k = half;
+    }
+    pt_neg(J[0], J[0]);
+    pt_to_affine_vt(*dst, J[0]);
+    delete[] J;
+}
+
 extern "C" {
 void hs_fp_mul(const fp *a, const fp *b, fp *r) { fp_mul(*r, *a, *b); }
 void hs_fp_add(const fp *a, const fp *b, fp *r) { fp_add(*r, *a, *b); }
@@ -98,6 +115,8 @@ void hs_aggregate_g2(const g2_aff *p, size_t n, g2_aff *out) {
     for (size_t i = 1; i < n; i++) { g2_jac t; pt_from_affine(t, p[i]); pt_add(acc, acc, t); }
     pt_to_affine(*out, acc);
 }
+void hs_subtract_g1(g1_aff *dst, const g1_aff *p, size_t n) { hs_subtract<fp>(dst, p, n); }
+void hs_subtract_g2(g2_aff *dst, const g2_aff *p, size_t n) { hs_subtract<fp2>(dst, p, n); }
 
 // ---- fpprog.hpp: execute a compiled tail program on the CPU exactly as k_fp_program does on the device ----
 static void run_program(const std::vector<uint32_t> &w, const fp *in0, const fp *in1, const fp *cst, fp *out0) {

@@ -83,6 +83,35 @@ def test_aggregate_all(cache, br, n):
     assert bg.aggregateAll(cache, []) == (False, b"")
 
 
+@pytest.mark.parametrize("n", [1, 2, 5, 127, 512])
+def test_subtract_all(cache, br, n):
+    """subtractAll (blst_min_pubkey_sig_core.nim:197-209) against BLST's from_affine / add_or_double_affine / cneg chain."""
+    import nim_blscurve_b200 as bg
+    sets = br.make_sets(700, 24)
+    pks = [sets[i:i + 96] for i in range(0, len(sets), 320)]
+    sigs = [sets[i + 128:i + 320] for i in range(0, len(sets), 320)]
+    _, dpk = br.aggregate_g1(b"".join(pks))
+    _, dsig = br.aggregate_g2(b"".join(sigs))
+    epk, esig = (pks * (n // len(pks) + 1))[:n], (sigs * (n // len(sigs) + 1))[:n]
+    assert bg.subtractAll(cache, dpk, epk) == br.subtract_all(dpk, b"".join(epk))
+    assert bg.subtractAll(cache, dsig, esig) == br.subtract_all(dsig, b"".join(esig))
+    # dst at infinity, and an empty list (dst untouched, :199-200)
+    assert bg.subtractAll(cache, bytes(96), epk) == br.subtract_all(bytes(96), b"".join(epk))
+    assert bg.subtractAll(cache, dsig, []) == dsig
+
+
+def test_subtract_all_golden_and_infinity(cache):
+    import json, os
+    import nim_blscurve_b200 as bg
+    a = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "aggregate.json")))
+    pk, sg = bytes.fromhex(a["pubkeys"]), bytes.fromhex(a["signatures"])
+    pks, sgs = [pk[i:i + 96] for i in range(0, len(pk), 96)], [sg[i:i + 192] for i in range(0, len(sg), 192)]
+    assert bg.subtractAll(cache, bytes.fromhex(a["agg_pubkey"]), pks[:5]).hex() == a["sub5_pubkey"]
+    assert bg.subtractAll(cache, bytes.fromhex(a["agg_signature"]), sgs[:5]).hex() == a["sub5_signature"]
+    assert bg.subtractAll(cache, bytes.fromhex(a["agg_pubkey"]), pks) == bytes(96)          # P - P = infinity
+    assert bg.subtractAll(cache, sgs[0], sgs[:1]) == bytes(192)
+
+
 def test_imad_peak_runs(cache):
     import nim_blscurve_b200 as bg
     r = bg.lib().blsgpu_imad_peak(cache.handle, 1)

@@ -166,6 +166,27 @@ def test_aggregate_golden(hs):
     assert pr.g1_from_mem(bytes(o1)) == pr.g1_mul(pr.g1_from_mem(pk[:96]), 2)
 
 
+def test_subtract_all_golden(hs):
+    """subtractAll (blst_min_pubkey_sig_core.nim:197-209) in the arrangement blsgpu_subtract_g1/_g2 launch."""
+    a = json.load(open(os.path.join(GOLD, "aggregate.json")))
+    pk, sg = bytes.fromhex(a["pubkeys"]), bytes.fromhex(a["signatures"])
+    d1 = (C.c_uint8 * 96).from_buffer_copy(bytes.fromhex(a["agg_pubkey"]))
+    d2 = (C.c_uint8 * 192).from_buffer_copy(bytes.fromhex(a["agg_signature"]))
+    hs.hs_subtract_g1(d1, buf(pk), C.c_size_t(5))
+    hs.hs_subtract_g2(d2, buf(sg), C.c_size_t(5))
+    assert bytes(d1).hex() == a["sub5_pubkey"] and bytes(d2).hex() == a["sub5_signature"]
+    # everything subtracted: infinity is the all-zero affine point; then infinity minus a point is its negative
+    hs.hs_subtract_g1(d1, buf(pk[5 * 96:]), C.c_size_t(7))
+    assert bytes(d1) == bytes(96)
+    hs.hs_subtract_g1(d1, buf(pk[:96]), C.c_size_t(1))
+    x, y = pr.g1_from_mem(pk[:96])
+    assert pr.g1_from_mem(bytes(d1)) == (x, (-y) % pr.P)
+    # dst equal to the only element: the doubling branch of the addition must not be taken for P + (-P)
+    d1 = (C.c_uint8 * 96).from_buffer_copy(pk[:96])
+    hs.hs_subtract_g1(d1, buf(pk[:96]), C.c_size_t(1))
+    assert bytes(d1) == bytes(96)
+
+
 def test_tail_programs(hs):
     """fpprog.hpp: the compiled warp-cooperative tail programs (final exponentiation of a product of partials, Horner
     over Miller-loop segments), executed round by round like k_fp_program, equal the straight-line formulas."""

@@ -71,8 +71,12 @@ def main():
     sets = br.make_sets(500, 12)
     pks = b"".join(sets[i:i + 96] for i in range(0, len(sets), 320))
     sigs = b"".join(sets[i + 128:i + 320] for i in range(0, len(sets), 320))
-    json.dump({"pubkeys": pks.hex(), "agg_pubkey": br.aggregate_g1(pks)[1].hex(),
-               "signatures": sigs.hex(), "agg_signature": br.aggregate_g2(sigs)[1].hex()},
+    agg_pk, agg_sig = br.aggregate_g1(pks)[1], br.aggregate_g2(sigs)[1]
+    # subtractAll (blst_min_pubkey_sig_core.nim:197-209): the aggregate minus its first five members
+    json.dump({"pubkeys": pks.hex(), "agg_pubkey": agg_pk.hex(),
+               "signatures": sigs.hex(), "agg_signature": agg_sig.hex(),
+               "sub5_pubkey": br.subtract_all(agg_pk, pks[:5 * 96]).hex(),
+               "sub5_signature": br.subtract_all(agg_sig, sigs[:5 * 192]).hex()},
               open(os.path.join(GOLD, "aggregate.json"), "w"))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
