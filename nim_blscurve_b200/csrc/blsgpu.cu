@@ -66,10 +66,11 @@ struct blsgpu_ctx {
     fp *d_consts = nullptr;                                  // Frobenius coefficients (fpprog::CONST_*)
     fp12 *d_gt = nullptr;                                    // final exponentiation result, Montgomery form
     bool serial_tail = false;
+    bool prog_smem_raised = false;                           // k_fp_program allowed > 48 KiB of shared memory on this device
     std::string err;
 };
 
-static std::string g_err;
+static thread_local std::string g_err;                   // blsgpu_create failures, read back by the calling thread
 
 static int fail(blsgpu_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
     char buf[512];
@@ -273,8 +274,8 @@ static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &ou
 static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp *in0, fp *out0, const fp *in1 = nullptr) {
     size_t smem = (size_t)p.nslots * sizeof(fp);
     if (smem > 48 * 1024) {
-        static bool raised = false;
-        if (!raised) { CK(cudaFuncSetAttribute(k_fp_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); raised = true; }
+        // per context, not per process: the attribute belongs to the function on ONE device
+        if (!ctx->prog_smem_raised) { CK(cudaFuncSetAttribute(k_fp_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); ctx->prog_smem_raised = true; }
     }
     k_fp_program<<<1, 32, smem, ctx->stream>>>(p.d, in0, in1, ctx->d_consts, out0, 0, 0, 0);
     ctx->launches++;

@@ -157,3 +157,72 @@ def test_combine_same_message(cache, br, srb, n):
     if n >= 2:
         bad = bg.MultiSignatureSet(pks, msg, sigs[1:] + sigs[:1]).combine(cache, srb)
         assert bg.batchVerifySerial(cache, [bad], srb) is False
+
+
+def test_concurrent_caches_from_host_threads(br, srb):
+    """SURVEY §8(b) threading: concurrent callers each own a cache (bls_batch_verifier.nim:389-391).  Four host
+    threads, four contexts on one device, different batch sizes (both kernel routes) and a corrupted batch, several
+    rounds at once: every call returns the verdict and GT bytes BLST gives for its batch."""
+    import threading
+    import nim_blscurve_b200 as bg
+    jobs = []
+    for t, (n, chunks) in enumerate([(5, 0), (129, 4), (700, 16), (4300, 8)]):
+        sets = br.make_sets(3000 + 5000 * t, n)
+        if t % 2:
+            sets = sets[:320 + 128] + sets[128:320] + sets[640:]      # set 1 carries set 0's signature
+        jobs.append((sets, chunks, br.batch_verify(sets, srb, chunks)))
+    assert [j[2][0] for j in jobs] == [True, False, True, False]
+    errors = []
+    start = threading.Barrier(len(jobs))
+
+    def worker(sets, chunks, want):
+        try:
+            c = bg.BatchedBLSVerifierCache(max_sets=len(sets) // 320, device=0)
+            start.wait()
+            for _ in range(4):
+                got = c.verify_raw(sets, srb, chunks, want_gt=True)
+                if got != want:
+                    errors.append((len(sets) // 320, got[0], want[0]))
+            c.close()
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+            start.abort()
+
+    th = [threading.Thread(target=worker, args=j) for j in jobs]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert errors == []
+
+
+def test_contexts_on_two_devices_in_one_process(br, srb):
+    """One host process driving several GPUs (a Nim application holds one cache per device): contexts on devices 0 and 1
+    used alternately and then from two threads, small and large route, give BLST's verdict and GT bytes on both."""
+    import threading
+    import nim_blscurve_b200 as bg
+    if bg.lib().blsgpu_device_count() < 2:
+        pytest.skip("needs two devices")
+    caches = [bg.BatchedBLSVerifierCache(max_sets=4300, device=d) for d in (0, 1)]
+    cases = []
+    for n, chunks in [(9, 0), (129, 4), (4300, 8)]:
+        sets = br.make_sets(900 + n, n)
+        cases.append((sets, chunks, br.batch_verify(sets, srb, chunks)))
+    for sets, chunks, want in cases:
+        for c in caches:
+            assert c.verify_raw(sets, srb, chunks, want_gt=True) == want
+    errors = []
+
+    def worker(c):
+        for sets, chunks, want in cases * 2:
+            if c.verify_raw(sets, srb, chunks, want_gt=True) != want:
+                errors.append(len(sets) // 320)
+
+    th = [threading.Thread(target=worker, args=(c,)) for c in caches]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for c in caches:
+        c.close()
+    assert errors == []
