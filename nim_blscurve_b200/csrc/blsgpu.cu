@@ -640,6 +640,10 @@ extern "C" int blsgpu_batch_verify(blsgpu_ctx *ctx, const void *sets, size_t n, 
     if (n == 0) return 0;
     if (!sets) return fail(ctx, BLSGPU_ERR_ARG, "sets is NULL");
     if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
+    // argument errors are reported before the copy is queued: no transfer from the caller's buffer outlives the call
+    if (!scalars && !srb) return fail(ctx, BLSGPU_ERR_ARG, "secureRandomBytes is NULL");
+    if (scalars)
+        for (size_t i = 0; i < n; i++) if (scalars[i] == 0) return fail(ctx, BLSGPU_ERR_ARG, "explicit RLC scalar is zero");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->d_sets, sets, n * sizeof(sigset), cudaMemcpyHostToDevice, ctx->stream));
     return blsgpu_batch_verify_dev(ctx, ctx->d_sets, n, srb, chunks, scalars, gt_out);

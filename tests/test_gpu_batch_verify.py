@@ -226,3 +226,33 @@ def test_contexts_on_two_devices_in_one_process(br, srb):
     for c in caches:
         c.close()
     assert errors == []
+
+
+def test_error_convention_of_the_c_abi(br, srb):
+    """SURVEY §8(b) error convention: argument / capacity problems are distinct negative codes with a message, never a
+    verdict, and a context keeps working after one (the reference doAsserts on an undersized cache,
+    bls_batch_verifier.nim:141, :319)."""
+    import ctypes as C
+    import nim_blscurve_b200 as bg
+    L = bg.lib()
+    ERR_ARG, ERR_CAPACITY = -2, -3                                   # include/blsgpu.h
+    assert L.blsgpu_create(10 ** 6, 16) is None
+    assert b"bad device" in L.blsgpu_last_error(None)
+    h = L.blsgpu_create(0, 16)
+    assert h and L.blsgpu_capacity(h) == 16
+    sets = br.make_sets(40, 17)
+    gt = (C.c_uint8 * 576)()
+    assert L.blsgpu_batch_verify(h, sets, 17, srb, 0, None, gt) == ERR_CAPACITY
+    assert b"capacity" in L.blsgpu_last_error(h)
+    assert L.blsgpu_batch_verify(h, None, 4, srb, 0, None, gt) == ERR_ARG
+    assert L.blsgpu_batch_verify(h, sets, 4, None, 0, None, gt) == ERR_ARG
+    assert L.blsgpu_batch_verify(h, sets, 4, srb, 0, (C.c_uint64 * 4)(1, 2, 0, 4), gt) == ERR_ARG      # zero scalar
+    assert L.blsgpu_batch_verify(None, sets, 4, srb, 0, None, gt) == ERR_ARG
+    assert L.blsgpu_batch_verify(h, sets, 0, srb, 0, None, gt) == 0                                   # empty -> false (:137-139)
+    assert L.blsgpu_rlc_scalars(h, srb, 17, 0, (C.c_uint64 * 17)()) == ERR_CAPACITY
+    assert L.blsgpu_hash_to_g2(h, b"x", 1, 1, b"d" * 256, 256, None, (C.c_uint8 * 192)()) == ERR_ARG  # DST > 255
+    assert L.blsgpu_subtract_g1(h, None, sets[:96], 1) == ERR_ARG
+    # the context is still good
+    assert L.blsgpu_batch_verify(h, sets, 16, srb, 4, None, gt) == 1
+    assert (True, bytes(gt)) == br.batch_verify(sets[:16 * 320], srb, 4)
+    L.blsgpu_destroy(h)
