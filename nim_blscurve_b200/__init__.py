@@ -13,4 +13,4 @@ from .batch_verifier import (  # noqa: F401
     batchVerifySerial, hashToG2, msmG1, msmG2, rlcScalars, aggregateVerify, verify, fastAggregateVerify, aggregateAllSegments, subtractAll,
     publicKeysFromBytes, signaturesFromBytes, publicKeysToBytes, signaturesToBytes,
 )
-from .multi_gpu import GpuBackend, batch_verify_distributed, shard_range  # noqa: F401,E402
+from .multi_gpu import GpuBackend, batch_verify_distributed, msm_g1_distributed, shard_range  # noqa: F401,E402

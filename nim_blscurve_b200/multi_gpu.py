@@ -47,6 +47,38 @@ class GpuBackend:
         return bool(rc), bytes(gt)
 
 
+    def msm_g1(self, points96: bytes, scalars: bytes, nbits: int) -> bytes:
+        from .batch_verifier import msmG1
+        return msmG1(self.cache, points96, scalars, nbits)
+
+    def aggregate_g1(self, points96: bytes) -> bytes:
+        from .batch_verifier import aggregateAll
+        ok, pt = aggregateAll(self.cache, [points96[i:i + 96] for i in range(0, len(points96), 96)])
+        return pt if ok else bytes(96)
+
+
+def msm_g1_distributed(backend, local_points96: bytes, local_scalars: bytes, nbits: int = 255, group=None) -> bytes:
+    """Collective G1 MSM (MSM row): every rank passes its slice of the points and scalars
+    (shard_range of the n inputs), runs the Pippenger MSM of blst_p1s_mult_pippenger (multi_scalar.c:415-434) on it
+    and contributes ONE point; the points are all-gathered (96 bytes per rank: the affine form, so that an empty or
+    cancelling share is the all-zero point) and summed on every rank.  Affine coordinates are unique, so the result
+    is byte-identical to the one-context MSM whatever the number of ranks."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n = len(local_points96) // 96
+    assert len(local_scalars) * 96 == len(local_points96) * ((nbits + 7) // 8)
+    mine = backend.msm_g1(local_points96, local_scalars, nbits) if n else bytes(96)
+    if world == 1:
+        return mine
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    gathered = torch.empty(world * 96, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, t, group=group)
+    return backend.aggregate_g1(gathered.cpu().numpy().tobytes())
+
+
 def batch_verify_distributed(backend, local_sets: bytes, first: int, total_n: int, srb: bytes, chunks: int,
                              group=None, want_gt: bool = False):
     """Collective call: every rank passes its share (global indices [first, first+len)) and gets the verdict.

@@ -161,3 +161,19 @@ def test_msm_g1_size_independent_properties(cache, br):
     pts = dp[96 * lo:96 * (lo + cnt)].cpu().numpy().tobytes()
     sc = ds[32 * lo:32 * (lo + cnt)].cpu().numpy().tobytes()
     assert parts[3] == br.msm_g1(pts, sc, 255)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_msm_rank_shares_on_one_device(cache, br, world):
+    """SURVEY.md §8e MSM row on one device: the per-rank MSMs over shard_range slices, summed by aggregateAll as
+    msm_g1_distributed does after its all-gather, equal blst_p1s_mult_pippenger over all points (n = 5 leaves ranks
+    with an empty share at world 8)."""
+    import nim_blscurve_b200 as bg
+    be = bg.GpuBackend(cache)
+    for n in (5, 1000):
+        pts, sc = br.msm_points(77, n)
+        parts = b""
+        for r in range(world):
+            f, c = bg.shard_range(n, world, r)
+            parts += bg.msm_g1_distributed(be, pts[f * 96:(f + c) * 96], sc[f * 32:(f + c) * 32], 255)   # world-1 path
+        assert be.aggregate_g1(parts) == br.msm_g1(pts, sc, 255)

@@ -3,7 +3,9 @@ over WORLD_SIZE ranks, NCCL all-gather of the 576-byte partials (nim_blscurve_b2
 
 Checks, on every rank: (1) the valid batch verifies; (2) with one corrupted set the verdict is false and the GT equals
 the one a single context computes for the whole batch on rank 0's GPU (independent of the number of ranks);
-(3) when oracle/_ref is present, rank 0 also compares that GT with BLST's for a 2 048-set prefix batch.
+(3) when oracle/_ref is present, rank 0 also compares that GT with BLST's for a 2 048-set prefix batch; (4) a G1 MSM
+of 16 384 points sharded over the ranks (msm_g1_distributed: 96 bytes per rank over NCCL) equals the single-context MSM on
+every rank and blst_p1s_mult_pippenger on rank 0.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
       tools/nccl_parity.py [N]
@@ -60,8 +62,23 @@ def main():
             ref = "BLST GT identical on a %d-set window around the corrupted set" % m
         except ImportError as ex:
             ref = f"oracle unavailable: {ex}"
+    # SURVEY.md §8e MSM row: the G1 MSM sharded the same way, one 96-byte point per rank over NCCL
+    msm = "skipped (oracle unavailable)"
+    try:
+        from oracle import blst_ref as br
+        m = 16384
+        pts, sc = br.msm_points(0xFACADE, m, 8)
+        f, c = bg.shard_range(m, world, rank)
+        got = bg.msm_g1_distributed(be, pts[f * 96:(f + c) * 96], sc[f * 32:(f + c) * 32], 255)
+        assert got == bg.msmG1(cache, pts, sc, 255), f"rank {rank}: sharded MSM differs from the single-context MSM"
+        if rank == 0:
+            assert got == br.msm_g1(pts, sc, 255), "sharded MSM differs from blst_p1s_mult_pippenger"
+        msm = f"G1 MSM of {m} points over {world} ranks == single context == BLST ({got[:8].hex()}...)"
+    except ImportError:
+        pass
     dist.barrier()
     if rank == 0:
+        print(f"nccl_parity MSM: {msm}", flush=True)
         print(f"nccl_parity OK: {n} sets over {world} ranks, verdicts (True, False), sharded GT == single-context GT "
               f"({gt_bad[:8].hex()}...); {ref}", flush=True)
     dist.destroy_process_group()
