@@ -21,7 +21,7 @@
 namespace fpprog {
 
 enum { OP_NOP = 0, OP_MUL = 1, OP_ADD = 2, OP_SUB = 3, OP_LEAF = 4 };
-enum { LANES = 32, MAX_SLOTS = 1024, ROUND_WORDS = LANES };
+enum { LANES = 32, MAX_SLOTS = 1024, ROUND_WORDS = LANES, LIN_DEFER = 1 };
 // buffer ids of the I/O tables
 enum { BUF_IN0 = 0, BUF_IN1 = 1, BUF_CONST = 2, BUF_OUT0 = 3 };
 // fp indices inside the constant pool (BUF_CONST): Frobenius coefficients as fp2 = 2 fp each
@@ -188,23 +188,31 @@ inline V12 frob(V12 a, int n) {
     return {{dst[0], dst[1], dst[2]}, {dst[3], dst[4], dst[5]}};
 }
 
+// (a + b v)^2 in Fp4 = Fp2[v]/(v^2 - xi): t0 = a^2 + xi b^2, t1 = 2 a b.  All ten Fp products come straight from the
+// coordinates (schoolbook, 2ab as a product instead of (a+b)^2 - a^2 - b^2): the three Fp4 squarings of a cyclotomic
+// squaring are 30 independent multiplications = ONE round of the 32 lanes with no addition level before it and three
+// after, where the Karatsuba forms needed two levels before and three after.  Same field elements, shorter schedule.
 inline void fp4_sqr(V2 &t0, V2 &t1, V2 a, V2 b) {
-    V2 a2 = sqr(a), b2 = sqr(b);
-    t1 = sqr(a + b) - a2 - b2;
+    V s0 = a.c0 * a.c0, s1 = a.c1 * a.c1, st = a.c0 * a.c1;
+    V r0 = b.c0 * b.c0, r1 = b.c1 * b.c1, rt = b.c0 * b.c1;
+    V p0 = a.c0 * b.c0, p1 = a.c1 * b.c1, p2 = a.c0 * b.c1, p3 = a.c1 * b.c0;
+    V2 a2 = {s0 - s1, st + st}, b2 = {r0 - r1, rt + rt}, ab = {p0 - p1, p2 + p3};
+    t1 = ab + ab;
     t0 = a2 + mul_xi(b2);
 }
 inline V12 cyc_sqr(V12 a) {                                             // Granger-Scott, as fp12_cyc_sqr
     V2 z0 = a.c0.c0, z4 = a.c0.c1, z3 = a.c0.c2, z2 = a.c1.c0, z1 = a.c1.c1, z5 = a.c1.c2, t0, t1, t2, t3;
+    // 3 t -+ 2 z as (t + t) + (t -+ 2z): 2z does not depend on the products, so two addition levels follow t, not three
     fp4_sqr(t0, t1, z0, z1);
-    z0 = dbl(t0 - z0) + t0;
-    z1 = dbl(t1 + z1) + t1;
+    z0 = dbl(t0) + (t0 - dbl(z0));
+    z1 = dbl(t1) + (t1 + dbl(z1));
     fp4_sqr(t0, t1, z2, z3);
     fp4_sqr(t2, t3, z4, z5);
-    z4 = dbl(t0 - z4) + t0;
-    z5 = dbl(t1 + z5) + t1;
+    z4 = dbl(t0) + (t0 - dbl(z4));
+    z5 = dbl(t1) + (t1 + dbl(z5));
     t3 = mul_xi(t3);
-    z2 = dbl(t3 + z2) + t3;
-    z3 = dbl(t2 - z3) + t2;
+    z2 = dbl(t3) + (t3 + dbl(z2));
+    z3 = dbl(t2) + (t2 - dbl(z3));
     return {{z0, z4, z3}, {z2, z1, z5}};
 }
 
@@ -284,7 +292,10 @@ inline Program compile(const Builder &B, int slack = 40) {
     std::vector<char> round_is_mul;
     while (!q_mul.empty() || !q_lin.empty()) {
         int hmax = std::max(q_mul.empty() ? -1 : q_mul.top().first, q_lin.empty() ? -1 : q_lin.top().first);
-        bool is_mul = q_lin.empty() || q_lin.top().first < hmax - slack;
+        // a ready add/sub that is less urgent than every ready multiplication (it is not on their way) does not get a
+        // round of its own: it joins the next addition round
+        bool is_mul = q_lin.empty() || q_lin.top().first < hmax - slack ||
+                      (!q_mul.empty() && q_lin.top().first + LIN_DEFER <= q_mul.top().first);
         std::priority_queue<PQE> &q = is_mul ? q_mul : q_lin;
         std::vector<int> ops;
         while (!q.empty() && (int)ops.size() < LANES && q.top().first >= hmax - slack) { ops.push_back(-q.top().second); q.pop(); }
