@@ -208,6 +208,7 @@ def test_tail_programs(hs):
         assert hs.hs_prog_final_split(buf(b"".join(f12b(x) for x in parts)), count, r2, stats) == 1
         assert bytes(r2) == bytes(r), count
         assert stats[2] <= 1024 and stats[1] < 950, list(stats)
+        assert stats[0] < 2600, list(stats)     # schedule length: 2 408-2 478 rounds (3 813 before the direct cyclotomic squaring)
     for nseg in (1, 2, 8, 21, 63):
         segs = b"".join(f12b(rnd12()) for _ in range(nseg))
         r, r2 = out(576), out(576)
