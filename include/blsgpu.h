@@ -49,6 +49,17 @@ void blsgpu_destroy(blsgpu_ctx *ctx);
 const char *blsgpu_last_error(const blsgpu_ctx *ctx);
 size_t blsgpu_capacity(const blsgpu_ctx *ctx);
 
+/* Multi-GPU context (`blsgpu_create(const int* devices, int ndev, size_t max_sets)`): replaces the
+ * Taskpools fan-out INSIDE the call (bls_batch_verifier.nim:316-369).  blsgpu_batch_verify on such a context cuts the
+ * batch into ndev balanced contiguous shares (the rule of parallel_chunks.nim:42-55), runs share k on devices[k]
+ * (scalars from the global derivation, so verdict and GT do not depend on ndev), pulls the ndev 576-byte Fp12
+ * partials + flags to devices[0] over NVLink peer copies and runs ONE final exponentiation.  blsgpu_msm_g1 /
+ * blsgpu_msm_g2 on such a context shard the points the same way (one affine partial sum per device, summed on
+ * devices[0]).  Every other entry point runs on devices[0].  A device may be listed more than once. */
+blsgpu_ctx *blsgpu_create_multi(const int *devices, int ndev, size_t max_sets);
+/* Number of shares (devices) a context spans: 1 for blsgpu_create. */
+int blsgpu_device_span(const blsgpu_ctx *ctx);
+
 /* Run on an existing CUDA stream (cudaStream_t passed as void*; NULL = the context's own stream). */
 int blsgpu_set_stream(blsgpu_ctx *ctx, void *cuda_stream);
 
@@ -94,7 +105,10 @@ int blsgpu_partial_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n, size_t fir
 int blsgpu_finalize_dev(blsgpu_ctx *ctx, const void *d_partials, size_t count, const int *d_flags,
                         uint8_t gt_out[576]);
 
-/* Product of `count` gathered partials, ONE final exponentiation, comparison with 1 (aggregate.c:494-500). */
+/* Product of `count` gathered partials, ONE final exponentiation, comparison with 1 (aggregate.c:494-500).
+ * The per-share flags returned by blsgpu_partial are NOT an input here: a caller that gathered a non-zero flag must
+ * report false without calling this (bls_batch_verifier.nim:153, :259), as multi_gpu.batch_verify_distributed does.
+ * blsgpu_finalize_dev takes the gathered flags (d_flags; NULL = the caller has checked them) and applies them itself. */
 int blsgpu_finalize(blsgpu_ctx *ctx, const uint8_t *partials, size_t count, uint8_t gt_out[576]);
 
 /* hash_to_G2 for n messages of msg_len bytes each (replaces blst_hash_to_g2 + blst_p2_to_affine,

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("BLSGPU_LIB") or os.path.join(_HERE, "libblsgpu.so")  
 
 # every symbol include/blsgpu.h declares (tests check the export list against the header)
 SYMBOLS = [
-    "blsgpu_device_count", "blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_capacity",
+    "blsgpu_device_count", "blsgpu_create", "blsgpu_create_multi", "blsgpu_device_span", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_capacity",
     "blsgpu_set_stream", "blsgpu_rlc_scalars", "blsgpu_batch_verify", "blsgpu_batch_verify_dev",
     "blsgpu_partial", "blsgpu_partial_dev", "blsgpu_finalize", "blsgpu_finalize_dev", "blsgpu_hash_to_g2", "blsgpu_aggregate_g1", "blsgpu_aggregate_g2",
     "blsgpu_msm_g1", "blsgpu_msm_g1_dev", "blsgpu_msm_g2", "blsgpu_msm_g2_dev", "blsgpu_combine", "blsgpu_last_stage_ms", "blsgpu_stage_name", "blsgpu_last_launches",
@@ -39,6 +39,9 @@ def lib():
     L.blsgpu_device_count.restype = C.c_int
     L.blsgpu_create.restype = vp
     L.blsgpu_create.argtypes = [C.c_int, sz]
+    L.blsgpu_create_multi.restype = vp
+    L.blsgpu_create_multi.argtypes = [vp, C.c_int, sz]
+    L.blsgpu_device_span.argtypes = [vp]
     L.blsgpu_destroy.argtypes = [vp]
     L.blsgpu_last_error.restype = C.c_char_p
     L.blsgpu_last_error.argtypes = [vp]

@@ -49,8 +49,8 @@ struct blsgpu_ctx {
     size_t misc_bytes = 0;
     void *d_misc2 = nullptr;      // small result scratch (MSM output)
     uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
-    cudaEvent_t ev[2 * ST_COUNT + 3];                        // stage begin/end pairs + fork/join/G1-ready
-    bool ev_valid[2 * ST_COUNT + 3];
+    cudaEvent_t ev[2 * ST_COUNT + 4];                        // stage begin/end pairs + fork/join/G1-ready
+    bool ev_valid[2 * ST_COUNT + 4];
     cudaStream_t side2 = nullptr;                            // small batches: [r_i] pk_i beside both the hash and the signature work
     cudaStream_t side = nullptr;                             // the signature-side MSM runs beside the per-set stages
     bool use_side = true;
@@ -67,6 +67,13 @@ struct blsgpu_ctx {
     fp12 *d_gt = nullptr;                                    // final exponentiation result, Montgomery form
     bool serial_tail = false;
     bool prog_smem_raised = false;                           // k_fp_program allowed > 48 KiB of shared memory on this device
+    // multi-device context (blsgpu_create_multi): this context is the leader (share 0 + the one final exponentiation),
+    // peers[k-1] owns share k on its own device; the 576-byte partials and the flags are gathered into the leader
+    std::vector<blsgpu_ctx *> peers;
+    fp12 *d_gather = nullptr;                                // ndev partials, share order
+    int *d_gather_flags = nullptr;                           // ndev infinite-public-key flags
+    cudaEvent_t ev_share = nullptr;                          // "this share's partial is ready" (recorded on the share's stream)
+    size_t multi_cap = 0;                                    // capacity of the whole multi-device context (leader only)
     std::string err;
 };
 
@@ -95,11 +102,15 @@ extern "C" int blsgpu_device_count(void) {
 }
 
 extern "C" const char *blsgpu_last_error(const blsgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
-extern "C" size_t blsgpu_capacity(const blsgpu_ctx *ctx) { return ctx ? ctx->cap : 0; }
+extern "C" size_t blsgpu_capacity(const blsgpu_ctx *ctx) { return ctx ? (ctx->multi_cap ? ctx->multi_cap : ctx->cap) : 0; }
 
 extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     if (!ctx) return;
+    for (blsgpu_ctx *p : ctx->peers) blsgpu_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_gather); cudaFree(ctx->d_gather_flags);
+    if (ctx->ev_share) cudaEventDestroy(ctx->ev_share);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_r); cudaFree(ctx->d_H); cudaFree(ctx->d_Pj); cudaFree(ctx->d_Q);
     cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gtb);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_consts); cudaFree(ctx->d_gt);
@@ -111,7 +122,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     cudaFree(ctx->d_norm); cudaFree(ctx->d_small); cudaFree(ctx->d_small_lines); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (int i = 0; i < 2 * ST_COUNT + 3; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2 * ST_COUNT + 4; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -126,7 +137,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     blsgpu_ctx *ctx = new blsgpu_ctx();
     ctx->device = device;
     ctx->cap = max_sets;
-    for (int i = 0; i < 2 * ST_COUNT + 3; i++) ctx->ev_valid[i] = false;
+    for (int i = 0; i < 2 * ST_COUNT + 4; i++) ctx->ev_valid[i] = false;
     for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
     cudaError_t e = cudaSetDevice(device);
     auto bad = [&](const char *what, cudaError_t err) {
@@ -175,15 +186,50 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bad("cudaDeviceSynchronize", e);
     ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
     if (getenv("BLSGPU_ACC_TEAM")) ctx->acc_team = atoi(getenv("BLSGPU_ACC_TEAM")) != 0;
-    for (int i = 0; i < 2 * ST_COUNT + 3; i++) {
+    for (int i = 0; i < 2 * ST_COUNT + 4; i++) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
         ctx->ev_valid[i] = true;
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
     if (getenv("BLSGPU_SIDE_STREAM")) ctx->use_side = atoi(getenv("BLSGPU_SIDE_STREAM")) != 0;
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_share, cudaEventDisableTiming)) != cudaSuccess) return bad("cudaEventCreate", e);
     return ctx;
 }
+
+// Multi-GPU behind the ABI: the fan-out that bls_batch_verifier.nim:316-369 does over Taskpools
+// threads happens over devices inside the call.  devices[0] hosts the leader (share 0, the gather target and the one
+// final exponentiation); a device index may be listed more than once (several shares on one GPU: the test boxes have one).
+extern "C" blsgpu_ctx *blsgpu_create_multi(const int *devices, int ndev, size_t max_sets) {
+    if (!devices || ndev <= 0 || ndev > 64) { fail(nullptr, 0, "blsgpu_create_multi: 1..64 devices"); return nullptr; }
+    if (max_sets == 0) max_sets = 1;
+    const size_t share = (max_sets + (size_t)ndev - 1) / (size_t)ndev;
+    blsgpu_ctx *lead = blsgpu_create(devices[0], ndev == 1 ? max_sets : share);
+    if (!lead) return nullptr;
+    for (int k = 1; k < ndev; k++) {
+        blsgpu_ctx *p = blsgpu_create(devices[k], share);
+        if (!p) { blsgpu_destroy(lead); return nullptr; }           // g_err holds the reason
+        lead->peers.push_back(p);
+    }
+    cudaError_t e = cudaSetDevice(lead->device);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&lead->d_gather, (size_t)ndev * sizeof(fp12));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&lead->d_gather_flags, (size_t)ndev * sizeof(int));
+    if (e != cudaSuccess) { fail(nullptr, 0, "blsgpu_create_multi: gather buffers", e); blsgpu_destroy(lead); return nullptr; }
+    // direct NVLink copies between the leader and every peer where the topology allows it (the 576-byte gather works
+    // without it too: cudaMemcpyPeerAsync stages through the host then)
+    for (blsgpu_ctx *p : lead->peers) {
+        if (p->device == lead->device) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, lead->device, p->device) == cudaSuccess && can) {
+            cudaSetDevice(lead->device);
+            if (cudaDeviceEnablePeerAccess(p->device, 0) != cudaSuccess) cudaGetLastError();   // already enabled is fine
+        }
+    }
+    cudaSetDevice(lead->device);
+    lead->multi_cap = ndev == 1 ? max_sets : share * (size_t)ndev;
+    return lead;
+}
+extern "C" int blsgpu_device_span(const blsgpu_ctx *ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
 
 extern "C" int blsgpu_set_stream(blsgpu_ctx *ctx, void *cuda_stream) {
     if (!ctx) return BLSGPU_ERR_ARG;
@@ -219,11 +265,11 @@ static words8 words_of(const uint8_t b[32]) {
 #define EV_FORK (2 * ST_COUNT)
 #define EV_JOIN (2 * ST_COUNT + 1)
 #define EV_G1 (2 * ST_COUNT + 2)
+#define EV_SC (2 * ST_COUNT + 3)
 
 // scalars for global indices [first, first+n) into d_r
 static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size_t first, size_t total_n,
-                          uint32_t chunks, const uint64_t *scalars) {
-    cudaStream_t s = ctx->stream;
+                          uint32_t chunks, const uint64_t *scalars, cudaStream_t s) {
     if (scalars) {
         for (size_t i = 0; i < n; i++) if (scalars[i] == 0) return fail(ctx, BLSGPU_ERR_ARG, "explicit RLC scalar is zero");
         CK(cudaMemcpyAsync(ctx->d_r, scalars, n * 8, cudaMemcpyHostToDevice, s));
@@ -453,29 +499,46 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
     return 0;
 }
 
-// all per-set stages + reductions; leaves the rank partial in d_partials[slot]
+static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t first, size_t total_n,
+                            const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, int slot);
+// all per-set stages + reductions; leaves the rank partial in d_partials[slot].  On failure nothing queued by the call
+// is left in flight (the side streams were forked off and the caller may free its buffers right after the error).
 static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t first, size_t total_n,
                        const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, int slot) {
+    int rc = run_partial_impl(ctx, d_sets, n, first, total_n, srb, chunks, scalars, slot);
+    if (rc) {
+        cudaStreamSynchronize(ctx->side);
+        cudaStreamSynchronize(ctx->side2);
+        cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t first, size_t total_n,
+                            const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, int slot) {
     cudaStream_t s = ctx->stream;
     ctx->launches = 0;
+    if (!scalars && !srb) return fail(ctx, BLSGPU_ERR_ARG, "secureRandomBytes is NULL");
     CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
-    BEGIN(ST_SCALARS, s);
-    int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars);
-    if (rc) return rc;
-    END(ST_SCALARS, s);
-    // fork: the signature-side sum only needs the scalars; it is latency-bound (bucket reduction, Horner) and hides
-    // behind the per-set stages on a second stream, joined before the Miller-loop lines
+    // fork: the scalar chain (strictly sequential SHA-256 per reference chunk: tens of milliseconds for a large batch
+    // when the caller passes tp.numThreads = 16..32 chunks) and the signature-side sum that consumes the scalars run on
+    // a second stream, beside H(m_i), which needs neither; [r_i]pk_i waits for the scalars, the Miller loop for the sum
     cudaStream_t g = ctx->use_side ? ctx->side : s;
     if (ctx->use_side) {
         CK(cudaEventRecord(ctx->ev[EV_FORK], s));
         CK(cudaStreamWaitEvent(g, ctx->ev[EV_FORK], 0));
     }
+    BEGIN(ST_SCALARS, g);
+    int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars, g);
+    if (rc) return rc;
+    END(ST_SCALARS, g);
+    if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_SC], g));
     // Small batches are latency chains (one thread per set): [r_i]pk_i does not depend on H(m_i), so it leads the
     // second stream instead of queueing behind the hash kernel.  Large batches fill the machine either way.
     const bool g1_aside = ctx->use_side && n < 2048;
     if (g1_aside) {
         cudaStream_t g1s = ctx->side2;
-        CK(cudaStreamWaitEvent(g1s, ctx->ev[EV_FORK], 0));
+        CK(cudaStreamWaitEvent(g1s, ctx->ev[EV_SC], 0));
         BEGIN(ST_G1MUL, g1s);
         k_g1_mul<<<nblk(n), 128, 0, g1s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
         END(ST_G1MUL, g1s);
@@ -545,6 +608,7 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     if (g1_aside) {
         CK(cudaStreamWaitEvent(s, ctx->ev[EV_G1], 0));
     } else {
+        if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_SC], 0));
         BEGIN(ST_G1MUL, s);
         k_g1_mul<<<nblk(n), 128, 0, s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
         END(ST_G1MUL, s);
@@ -589,7 +653,9 @@ static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_in
     CK(cudaStreamSynchronize(s));
     int flags[4];
     memcpy(flags, ctx->h_pinned + 576, sizeof flags);
-    if (pk_inf) *pk_inf = flags[0] | flags[2];
+    // the gathered per-share flags when the caller supplies them (finalize_dev), else this context's own flag from the
+    // run_partial that preceded (batch_verify_dev); never both: d_flags[0] may be stale from an earlier, unrelated batch
+    if (pk_inf) *pk_inf = d_rank_flags ? flags[2] : flags[0];
     if (gt_out) memcpy(gt_out, ctx->h_pinned, 576);
     return flags[1] ? 1 : 0;
 }
@@ -608,7 +674,7 @@ extern "C" int blsgpu_rlc_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t
     if (n == 0) return 0;
     if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
     CK(cudaSetDevice(ctx->device));
-    int rc = launch_scalars(ctx, srb, n, 0, n, chunks, nullptr);
+    int rc = launch_scalars(ctx, srb, n, 0, n, chunks, nullptr, ctx->stream);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out, ctx->d_r, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -633,13 +699,80 @@ extern "C" int blsgpu_batch_verify_dev(blsgpu_ctx *ctx, const void *d_sets, size
     return rc;
 }
 
+// balanced contiguous split, the rule of blscurve/parallel_chunks.nim:42-55 applied to devices
+static void share_range(size_t total, size_t parts, size_t k, size_t &first, size_t &len) {
+    const size_t base = total / parts, rem = total % parts;
+    if (k < rem) { first = (base + 1) * k; len = base + 1; }
+    else { first = base * k + rem; len = base; }
+}
+
+// One batch over every device of a multi-device context, inside ONE call: share k goes to device k (H2D from the
+// caller's buffer on that device's stream), every device leaves its 576-byte partial + flag in its own memory, the
+// leader's stream waits for each share's event and pulls them over NVLink (cudaMemcpyPeerAsync), then runs the one final
+// exponentiation.  Scalars come from the GLOBAL (n, chunks) derivation, so verdict and GT equal the one-device result.
+static int batch_verify_multi(blsgpu_ctx *lead, const uint8_t *sets, size_t n, const uint8_t srb[32], uint32_t chunks,
+                              const uint64_t *scalars, uint8_t gt_out[576]) {
+    blsgpu_ctx *ctx = lead;                                  // CK() reports into the leader
+    std::vector<blsgpu_ctx *> all;
+    all.push_back(lead);
+    for (blsgpu_ctx *p : lead->peers) all.push_back(p);
+    const size_t ndev = all.size();
+    int rc = 0, total_launches = 0;
+    size_t issued = 0;
+    for (size_t k = 0; k < ndev && rc == 0; k++) {
+        blsgpu_ctx *c = all[k];
+        size_t first, len;
+        share_range(n, ndev, k, first, len);
+        cudaError_t e = cudaSetDevice(c->device);
+        if (e != cudaSuccess) { rc = fail(lead, BLSGPU_ERR_CUDA, "cudaSetDevice", e); break; }
+        issued = k + 1;
+        if (len == 0) {                                      // more devices than sets: neutral partial
+            k_partial_one<<<1, 32, 0, c->stream>>>(c->d_partials, c->d_flags);
+            c->launches = 1;
+        } else {
+            e = cudaMemcpyAsync(c->d_sets, sets + first * sizeof(sigset), len * sizeof(sigset), cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) { rc = fail(lead, BLSGPU_ERR_CUDA, "cudaMemcpyAsync(share)", e); break; }
+            rc = run_partial(c, c->d_sets, len, first, n, srb, chunks, scalars ? scalars + first : nullptr, 0);
+            if (rc && c != lead) lead->err = c->err;
+        }
+        total_launches += c->launches;
+        if (rc == 0 && (e = cudaEventRecord(c->ev_share, c->stream)) != cudaSuccess) rc = fail(lead, BLSGPU_ERR_CUDA, "cudaEventRecord", e);
+    }
+    if (rc) {                                                // nothing of this call may outlive it: the caller owns `sets`
+        for (size_t k = 0; k < issued; k++) { cudaSetDevice(all[k]->device); cudaStreamSynchronize(all[k]->stream); }
+        cudaSetDevice(lead->device);
+        return rc;
+    }
+    CK(cudaSetDevice(lead->device));
+    for (size_t k = 0; k < ndev; k++) {
+        blsgpu_ctx *c = all[k];
+        CK(cudaStreamWaitEvent(lead->stream, c->ev_share, 0));
+        CK(cudaMemcpyPeerAsync(lead->d_gather + k, lead->device, c->d_partials, c->device, sizeof(fp12), lead->stream));
+        CK(cudaMemcpyPeerAsync(lead->d_gather_flags + k, lead->device, c->d_flags, c->device, sizeof(int), lead->stream));
+    }
+    int bad = 0;
+    rc = run_final(lead, (int)ndev, gt_out, &bad, lead->d_gather, lead->d_gather_flags);
+    lead->launches = total_launches + lead->launches;
+    collect_stage_times(lead, true);
+    // the H2D copies of the other devices read the caller's buffer: they are complete (their partials were consumed)
+    if (rc < 0) return rc;
+    if (bad) { if (gt_out) memset(gt_out, 0, 576); return 0; }
+    return rc;
+}
+
 extern "C" int blsgpu_batch_verify(blsgpu_ctx *ctx, const void *sets, size_t n, const uint8_t srb[32], uint32_t chunks,
                                    const uint64_t *scalars, uint8_t gt_out[576]) {
     if (!ctx) return BLSGPU_ERR_ARG;
     if (gt_out) memset(gt_out, 0, 576);
     if (n == 0) return 0;
     if (!sets) return fail(ctx, BLSGPU_ERR_ARG, "sets is NULL");
-    if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
+    if (n > blsgpu_capacity(ctx)) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
+    if (!ctx->peers.empty()) {
+        if (!scalars && !srb) return fail(ctx, BLSGPU_ERR_ARG, "secureRandomBytes is NULL");
+        if (scalars)
+            for (size_t i = 0; i < n; i++) if (scalars[i] == 0) return fail(ctx, BLSGPU_ERR_ARG, "explicit RLC scalar is zero");
+        return batch_verify_multi(ctx, (const uint8_t *)sets, n, srb, chunks, scalars, gt_out);
+    }
     // argument errors are reported before the copy is queued: no transfer from the caller's buffer outlives the call
     if (!scalars && !srb) return fail(ctx, BLSGPU_ERR_ARG, "secureRandomBytes is NULL");
     if (scalars)
@@ -713,7 +846,7 @@ extern "C" int blsgpu_finalize_dev(blsgpu_ctx *ctx, const void *d_partials, size
     if (count == 0) return 0;
     CK(cudaSetDevice(ctx->device));
     int bad = 0;
-    int rc = run_final(ctx, (int)count, gt_out, &bad, (const fp12 *)d_partials, d_flags);
+    int rc = run_final(ctx, (int)count, gt_out, d_flags ? &bad : nullptr, (const fp12 *)d_partials, d_flags);
     collect_stage_times(ctx, true);
     if (rc < 0) return rc;
     if (bad) { if (gt_out) memset(gt_out, 0, 576); return 0; }
@@ -1090,12 +1223,17 @@ static int msm_api_dev(blsgpu_ctx *ctx, const void *d_points, const void *d_scal
 }
 
 template <class F>
+static int msm_api_multi(blsgpu_ctx *lead, const uint8_t *points, const uint8_t *scalars, size_t n, size_t nbits, uint8_t *out);
+
+template <class F>
 static int msm_api_host(blsgpu_ctx *ctx, const void *points, const void *scalars, size_t n, size_t nbits, uint8_t *out) {
     const size_t pb = sizeof(aff_t<F>);
     if (!ctx || !out) return BLSGPU_ERR_ARG;
     memset(out, 0, pb);
     if (n == 0) return 0;
     if (!points || !scalars || nbits == 0 || nbits > 256) return fail(ctx, BLSGPU_ERR_ARG, "bad MSM arguments");
+    if (!ctx->peers.empty() && n >= 2 * (1 + ctx->peers.size()))
+        return msm_api_multi<F>(ctx, (const uint8_t *)points, (const uint8_t *)scalars, n, nbits, out);
     CK(cudaSetDevice(ctx->device));
     size_t sb = (nbits + 7) / 8;
     int rc = ensure_misc(ctx, n * pb + n * sb + 256);
@@ -1104,6 +1242,60 @@ static int msm_api_host(blsgpu_ctx *ctx, const void *points, const void *scalars
     CK(cudaMemcpyAsync(base, points, n * pb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(base + n * pb, scalars, n * sb, cudaMemcpyHostToDevice, ctx->stream));
     return msm_api_dev<F>(ctx, base, base + n * pb, n, nbits, out);
+}
+
+// MSM over every device of a multi-device context (MSM row): device k takes the k-th balanced
+// slice of the points and scalars and returns ONE affine point (unique coordinates: an empty or cancelling share is the
+// all-zero point); the leader sums the ndev points with the aggregateAll tree.  All devices are launched before any is
+// waited for.
+template <class F>
+static int msm_api_multi(blsgpu_ctx *lead, const uint8_t *points, const uint8_t *scalars, size_t n, size_t nbits, uint8_t *out) {
+    const size_t pb = sizeof(aff_t<F>), sb = (nbits + 7) / 8;
+    std::vector<blsgpu_ctx *> all;
+    all.push_back(lead);
+    for (blsgpu_ctx *p : lead->peers) all.push_back(p);
+    const size_t ndev = all.size();
+    std::vector<uint8_t> parts(ndev * pb, 0);
+    std::vector<char> busy(ndev, 0);
+    int rc = 0, launches = 0;
+    for (size_t k = 0; k < ndev && rc == 0; k++) {
+        blsgpu_ctx *ctx = all[k];
+        size_t first, len;
+        share_range(n, ndev, k, first, len);
+        if (len == 0) continue;
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) { rc = fail(lead, BLSGPU_ERR_CUDA, "cudaSetDevice", e); break; }
+        rc = ensure_misc(ctx, len * pb + len * sb + 256);
+        if (!rc) rc = ensure_misc2(ctx, 256);
+        if (rc) break;
+        uint8_t *base = (uint8_t *)ctx->d_misc;
+        if ((e = cudaMemcpyAsync(base, points + first * pb, len * pb, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(base + len * pb, scalars + first * sb, len * sb, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+            rc = fail(lead, BLSGPU_ERR_CUDA, "cudaMemcpyAsync(msm share)", e);
+            break;
+        }
+        busy[k] = 1;
+        std::string err;
+        ctx->launches = 0;
+        int r = msm_run<F>(ctx->msm, base, pb, base + len * pb, sb, len, (int)nbits, ctx->stream, nullptr, (aff_t<F> *)ctx->d_misc2,
+                           &ctx->launches, err);
+        if (r) { rc = fail(lead, r == -1 ? BLSGPU_ERR_CUDA : BLSGPU_ERR_ARG, err.c_str()); break; }
+        launches += ctx->launches;
+        if ((e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_misc2, pb, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
+            rc = fail(lead, BLSGPU_ERR_CUDA, "cudaMemcpyAsync(msm partial)", e);
+    }
+    for (size_t k = 0; k < ndev; k++) {
+        if (!busy[k]) continue;
+        cudaSetDevice(all[k]->device);
+        cudaError_t e = cudaStreamSynchronize(all[k]->stream);
+        if (e != cudaSuccess && rc == 0) rc = fail(lead, BLSGPU_ERR_CUDA, "cudaStreamSynchronize(msm share)", e);
+        if (rc == 0) memcpy(parts.data() + k * pb, all[k]->h_pinned, pb);
+    }
+    cudaSetDevice(lead->device);
+    if (rc) return rc;
+    rc = sizeof(F) == sizeof(fp) ? blsgpu_aggregate_g1(lead, parts.data(), ndev, out) : blsgpu_aggregate_g2(lead, parts.data(), ndev, out);
+    lead->launches = launches;
+    return rc;
 }
 
 extern "C" int blsgpu_msm_g1_dev(blsgpu_ctx *ctx, const void *d_points96, const void *d_scalars, size_t n, size_t nbits,

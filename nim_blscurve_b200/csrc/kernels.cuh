@@ -41,11 +41,14 @@ struct words8 { uint32_t w[8]; };   // a 32-byte string as big-endian words
 __device__ __forceinline__ void sha256_of_32(uint32_t *out, const uint32_t *in) {
     uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
     uint32_t w[16];
+#pragma unroll
     for (int i = 0; i < 8; i++) w[i] = in[i];
     w[8] = 0x80000000u;
+#pragma unroll
     for (int i = 9; i < 15; i++) w[i] = 0;
     w[15] = 256;
-    sha256_block(h, w);
+    sha256_block_regs(h, w);
+#pragma unroll
     for (int i = 0; i < 8; i++) out[i] = h[i];
 }
 
@@ -90,6 +93,7 @@ __global__ void k_rlc_scalars(words8 srb, size_t total_n, uint32_t chunks, size_
         do {
             uint32_t t[8];
             sha256_of_32(t, seed);
+#pragma unroll
             for (int k = 0; k < 8; k++) seed[k] = t[k];
             r = le64_of_be_words(seed);
         } while (r == 0);

@@ -2,7 +2,8 @@
 #
 # Same idioms as blscurve/blst/blst_abi.nim (importc, cdecl, raw pointers, `bool`-like cint results):
 # NOT compiled in the build container (no Nim toolchain there); kept in-tree as the reference-side binding
-# a maintainer adds.  See INTEGRATION.md.
+# a maintainer adds.  tests/test_abi_and_host.py parses this file and diffs every proc (name, arity, parameter and
+# result types) against include/blsgpu.h, so the two cannot drift apart silently.  See INTEGRATION.md.
 {.push raises: [].}
 
 const blsgpuLib* {.strdefine.} = "libblsgpu.so"
@@ -13,6 +14,8 @@ type
 {.push cdecl, dynlib: blsgpuLib, importc.}
 proc blsgpu_device_count*(): cint
 proc blsgpu_create*(device: cint, maxSets: csize_t): BlsGpuCtx
+proc blsgpu_create_multi*(devices: ptr cint, ndev: cint, maxSets: csize_t): BlsGpuCtx
+proc blsgpu_device_span*(ctx: BlsGpuCtx): cint
 proc blsgpu_destroy*(ctx: BlsGpuCtx)
 proc blsgpu_last_error*(ctx: BlsGpuCtx): cstring
 proc blsgpu_capacity*(ctx: BlsGpuCtx): csize_t
@@ -53,5 +56,17 @@ proc blsgpu_pubkeys_to_bytes*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: 
 proc blsgpu_signatures_to_bytes*(ctx: BlsGpuCtx, points: pointer, n: csize_t, dst: ptr byte): cint
 proc blsgpu_combine*(ctx: BlsGpuCtx, srb: ptr array[32, byte], pubkeys, sigs: pointer, n: csize_t,
                      pkOut, sigOut: pointer): cint
+proc blsgpu_msm_g1_dev*(ctx: BlsGpuCtx, dPoints, dScalars: pointer, n, nbits: csize_t, dst: pointer): cint
+proc blsgpu_msm_g2_dev*(ctx: BlsGpuCtx, dPoints, dScalars: pointer, n, nbits: csize_t, dst: pointer): cint
+proc blsgpu_last_stage_ms*(ctx: BlsGpuCtx, ms: ptr cfloat, max: cint): cint
+proc blsgpu_stage_name*(stage: cint): cstring
+proc blsgpu_last_launches*(ctx: BlsGpuCtx): cint
+# diagnostics / synthetic workloads (benchmarks and tests only)
+proc blsgpu_test_fp*(ctx: BlsGpuCtx, op: cint, a, b: pointer, n: csize_t, dst: pointer): cint
+proc blsgpu_test_small_hash*(ctx: BlsGpuCtx, sets: pointer, n: csize_t, outIn, outOut: ptr byte): cint
+proc blsgpu_imad_peak*(ctx: BlsGpuCtx, wide: cint): cdouble
+proc blsgpu_fpmul_peak*(ctx: BlsGpuCtx, threadsPerBlock, blocksPerSm: cint): cdouble
+proc blsgpu_make_sets*(ctx: BlsGpuCtx, seed: uint64, first, n: csize_t, dst: pointer, outOnDevice: cint): cint
+proc blsgpu_msm_make_inputs*(ctx: BlsGpuCtx, seed: uint64, n: csize_t, dPoints, dScalars: pointer): cint
 {.pop.}
 {.pop.}
