@@ -90,7 +90,10 @@ int blsgpu_batch_verify_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n, const
  * exactly those indices from the global (total_n, chunks) derivation, so the result does not depend on
  * the number of ranks.  Output: the 576-byte Fp12 partial  conj(ML(S_k, G1)) * prod_{i in k} ML([r_i]pk_i, H(m_i))
  * in the reference's in-memory Fp12 layout (what blst_pairing_merge multiplies, aggregate.c:410-458), and
- * *flags != 0 if a set of this share must fail the batch (infinite public key).
+ * *flags != 0 if a set of this share must fail the batch (infinite public key).  Such a share's partial is SEALED:
+ * it is the zero element of Fp12 (576 zero bytes), which absorbs the product of the gathered partials and which the
+ * final exponentiation maps to zero != one — so the partial alone carries the verdict and ranks need to exchange
+ * nothing else (one 576-byte collective); blsgpu_finalize* then return 0 with an all-zero GT.
  * sets_on_device != 0: `sets` is a device pointer. */
 int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_device, size_t n, size_t first, size_t total_n,
                    const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, uint8_t partial_out[576],
@@ -106,9 +109,9 @@ int blsgpu_finalize_dev(blsgpu_ctx *ctx, const void *d_partials, size_t count, c
                         uint8_t gt_out[576]);
 
 /* Product of `count` gathered partials, ONE final exponentiation, comparison with 1 (aggregate.c:494-500).
- * The per-share flags returned by blsgpu_partial are NOT an input here: a caller that gathered a non-zero flag must
- * report false without calling this (bls_batch_verifier.nim:153, :259), as multi_gpu.batch_verify_distributed does.
- * blsgpu_finalize_dev takes the gathered flags (d_flags; NULL = the caller has checked them) and applies them itself. */
+ * The per-share flags are not an input: a flagged share's partial is sealed (all zero, see blsgpu_partial), so the
+ * product is zero and the result is 0 / all-zero GT, the reference's `false` for an infinite public key
+ * (bls_batch_verifier.nim:153, :259).  blsgpu_finalize_dev additionally accepts gathered flags (d_flags, NULL = none). */
 int blsgpu_finalize(blsgpu_ctx *ctx, const uint8_t *partials, size_t count, uint8_t gt_out[576]);
 
 /* hash_to_G2 for n messages of msg_len bytes each (replaces blst_hash_to_g2 + blst_p2_to_affine,

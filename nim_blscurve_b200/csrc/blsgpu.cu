@@ -51,6 +51,8 @@ struct blsgpu_ctx {
     uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
     cudaEvent_t ev[2 * ST_COUNT + 4];                        // stage begin/end pairs + fork/join/G1-ready
     bool ev_valid[2 * ST_COUNT + 4];
+    cudaEvent_t ev_scratch[8];                               // event window of the deferred signature-pair Miller loop
+    bool ev_scratch_valid = false;
     cudaStream_t side2 = nullptr;                            // small batches: [r_i] pk_i beside both the hash and the signature work
     cudaStream_t side = nullptr;                             // the signature-side MSM runs beside the per-set stages
     bool use_side = true;
@@ -111,6 +113,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_gather); cudaFree(ctx->d_gather_flags);
     if (ctx->ev_share) cudaEventDestroy(ctx->ev_share);
+    if (ctx->ev_scratch_valid) for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev_scratch[i]);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_r); cudaFree(ctx->d_H); cudaFree(ctx->d_Pj); cudaFree(ctx->d_Q);
     cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gtb);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_consts); cudaFree(ctx->d_gt);
@@ -163,7 +166,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     // block products: <= 64 segments x (blocks per tile + 1) x tiles
     ctx->f_cap = (n + 1) / 2 + 40000 + 64 * ((n + 1) / LINES_TILE + 2);   // >= nseg * groups for every miller_shape
     ALLOC(ctx->d_F, ctx->f_cap * sizeof(fp12));
-    ctx->f2_cap = ctx->f_cap / 64 + 4096;
+    ctx->f2_cap = ctx->f_cap / 8 + 4096;                      // level-1 output of the 8-way product trees (+ padding)
     ALLOC(ctx->d_F2, ctx->f2_cap * sizeof(fp12));
     ALLOC(ctx->d_seg, 64 * sizeof(fp12));
     ALLOC(ctx->d_partials, 64 * sizeof(fp12));
@@ -194,6 +197,8 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     if ((e = cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
     if (getenv("BLSGPU_SIDE_STREAM")) ctx->use_side = atoi(getenv("BLSGPU_SIDE_STREAM")) != 0;
     if ((e = cudaEventCreateWithFlags(&ctx->ev_share, cudaEventDisableTiming)) != cudaSuccess) return bad("cudaEventCreate", e);
+    for (int i = 0; i < 8; i++) if ((e = cudaEventCreate(&ctx->ev_scratch[i])) != cudaSuccess) return bad("cudaEventCreate", e);
+    ctx->ev_scratch_valid = true;
     return ctx;
 }
 
@@ -397,8 +402,8 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
     if (nseg > 63) nseg = 63;
 }
 
-// Multi-Miller loop over the np pairs (d_Q[i], d_P[i]) + reductions; leaves conj(prod ML) in d_partials[slot]
-static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
+// Multi-Miller loop over the np pairs (d_Q[pair0 + i], d_P[pair0 + i]) + reductions; leaves conj(prod ML) in d_partials[slot]
+static int run_miller(blsgpu_ctx *ctx, size_t np, int slot, size_t pair0 = 0) {
     cudaStream_t s = ctx->stream;
     int rc;
     // tile by tile: lines, then per-(group, segment) accumulation
@@ -414,10 +419,11 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
     // small batches: the GT product of each segment row runs as product-tree programs over groups of 8 columns, so
     // the rows of d_F are padded to a multiple of 8 with ones
     static const int gt_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 15;   // bit 3: GT product
-    const bool gt_prog = (gt_env & 8) && team && np <= ctx->lines_cap && ncols <= 64 && !ctx->serial_tail;
+    static const size_t gt_prog_max = getenv("BLSGPU_GT_PROG_MAX") ? (size_t)atoll(getenv("BLSGPU_GT_PROG_MAX")) : ((size_t)1 << 20);
+    const bool gt_prog = (gt_env & 8) && team && np <= ctx->lines_cap && ncols <= gt_prog_max && !ctx->serial_tail;
     const size_t row_stride = gt_prog && ncols > 8 ? ((ncols + 7) & ~(size_t)7) : ncols;
-    const size_t ncols2 = (ncols + BLS_ACC_BS - 1) / BLS_ACC_BS;
-    if ((size_t)nseg * ncols > ctx->f_cap || (size_t)nseg * ncols2 > ctx->f2_cap)
+    const size_t ncols2 = gt_prog ? ((((ncols + 7) / 8) + 7) & ~(size_t)7) : (ncols + BLS_ACC_BS - 1) / BLS_ACC_BS;
+    if ((size_t)nseg * row_stride > ctx->f_cap || (size_t)nseg * ncols2 > ctx->f2_cap)
         return fail(ctx, BLSGPU_ERR_CAPACITY, "segment product buffer too small");
     size_t col = 0;
     BEGIN(ST_LINES, s);
@@ -434,12 +440,12 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
             if (rc) return rc;
             const size_t per = (size_t)ML_NLINES * 6;
             if (!ctx->d_small_lines) CK(cudaMalloc((void **)&ctx->d_small_lines, small_lines_max() * per * sizeof(fp)));
-            launch_prog_many(ctx, lp, s, t, (const fp *)ctx->d_Q, 4, (const fp *)ctx->d_P, 2, ctx->d_small_lines, per, true);
-            k_lines_from_prog<<<nblk(t * ML_NLINES * ML_LINE_WORDS, 256), 256, 0, s>>>((const uint32_t *)ctx->d_small_lines, ctx->d_Q, ctx->d_P, t,
+            launch_prog_many(ctx, lp, s, t, (const fp *)(ctx->d_Q + pair0), 4, (const fp *)(ctx->d_P + pair0), 2, ctx->d_small_lines, per, true);
+            k_lines_from_prog<<<nblk(t * ML_NLINES * ML_LINE_WORDS, 256), 256, 0, s>>>((const uint32_t *)ctx->d_small_lines, ctx->d_Q + pair0, ctx->d_P + pair0, t,
                                                                                       ctx->d_lines, stride);
             ctx->launches++;
         } else {
-            k_miller_lines<<<nblk(t), 128, 0, s>>>(ctx->d_Q + off, ctx->d_P + off, t, ctx->d_lines, stride);
+            k_miller_lines<<<nblk(t), 128, 0, s>>>(ctx->d_Q + pair0 + off, ctx->d_P + pair0 + off, t, ctx->d_lines, stride);
         }
         if (single) { END(ST_LINES, s); BEGIN(ST_ACC, s); }
         size_t ngroups = (t + G - 1) / G;
@@ -457,22 +463,33 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot) {
     if (!single) { END(ST_LINES, s); BEGIN(ST_ACC, s); }    // multi-tile: lines+acc are reported together under miller_lines
     END(ST_ACC, s);
     BEGIN(ST_GTPROD, s);
-    if (gt_prog) {
+    if (ncols == 1) {                                       // one group: the segment values are the products already
+        CK(cudaMemcpy2DAsync(ctx->d_seg, sizeof(fp12), ctx->d_F, row_stride * sizeof(fp12), sizeof(fp12), (size_t)nseg,
+                             cudaMemcpyDeviceToDevice, s));
+    } else if (gt_prog) {
+        // product trees of eight as dataflow programs, one warp per (segment row, group of 8 columns), level after level
+        // (the 54 multiplications of a tree node spread over the 32 lanes); the rows ping-pong between d_F and d_F2 and
+        // every level's rows are padded with ones to a multiple of 8
         blsgpu_ctx::dev_prog p8, pm;
-        if (ncols <= 8) {
-            rc = get_prog(ctx, 4, (int)ncols, pm);
-            if (rc) return rc;
-            launch_prog_many(ctx, pm, s, (size_t)nseg, (const fp *)ctx->d_F, 12 * ncols, nullptr, 0, (fp *)ctx->d_seg, 12);
-        } else {
-            const int m = (int)(row_stride / 8);
+        fp12 *cur = ctx->d_F, *other = ctx->d_F2;
+        size_t cols = ncols, stride = row_stride;
+        while (cols > 8) {
+            const size_t m = (cols + 7) / 8, m_stride = m > 8 ? ((m + 7) & ~(size_t)7) : m;
             rc = get_prog(ctx, 4, 8, p8);
-            if (!rc) rc = get_prog(ctx, 4, m, pm);
             if (rc) return rc;
-            k_fp12_pad_one<<<nseg, 32, 0, s>>>(ctx->d_F, row_stride, ncols);
-            launch_prog_many(ctx, p8, s, (size_t)nseg * m, (const fp *)ctx->d_F, 96, nullptr, 0, (fp *)ctx->d_F2, 12);
-            launch_prog_many(ctx, pm, s, (size_t)nseg, (const fp *)ctx->d_F2, 12 * (size_t)m, nullptr, 0, (fp *)ctx->d_seg, 12);
+            if (cols & 7) { k_fp12_pad_one<<<nseg, 32, 0, s>>>(cur, stride, cols); ctx->launches++; }
+            k_fp_program_rows<<<(unsigned)((size_t)nseg * m), 32, (size_t)p8.nslots * sizeof(fp), s>>>(
+                p8.d, (const fp *)cur, ctx->d_consts, (fp *)other, (unsigned)m, stride, m_stride);
             ctx->launches++;
+            fp12 *t = cur; cur = other; other = t;
+            cols = m;
+            stride = m_stride;
         }
+        rc = get_prog(ctx, 4, (int)cols, pm);
+        if (rc) return rc;
+        k_fp_program_rows<<<(unsigned)nseg, 32, (size_t)pm.nslots * sizeof(fp), s>>>(pm.d, (const fp *)cur, ctx->d_consts,
+                                                                                    (fp *)ctx->d_seg, 1u, stride, 1);
+        ctx->launches++;
     } else if (ncols > BLS_ACC_BS) {
         dim3 grid((unsigned)ncols2, nseg);
         k_fp12_rows_step<<<grid, BLS_ACC_BS, 0, s>>>(ctx->d_F, ncols, ncols, ctx->d_F2, ncols2);
@@ -620,8 +637,37 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     else k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 0, 0);
     END(ST_AFFINE, s);
     ctx->launches += 3;
-    if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));   // join: pair number n is in place
-    return run_miller(ctx, n + 1, slot);
+    // Large batches behind long scalar chains (the caller's tp.numThreads = 16..32 chunks: tens of milliseconds of
+    // sequential SHA-256, then the signature-side MSM): the n set pairs do not wait for the signature sum.  Their
+    // multi-Miller loop runs first; pair number n = (S, -G1) gets its own small Miller loop after the join and the two
+    // values are multiplied (one Fp12 product program).  Same product of the same n + 1 Miller values, hence same GT.
+    static const size_t defer_min = getenv("BLSGPU_DEFER_SIG_MIN") ? (size_t)atoll(getenv("BLSGPU_DEFER_SIG_MIN")) : 16384;
+    const size_t nchunks = chunks == 0 ? 1 : (total_n < chunks ? total_n : (size_t)chunks);
+    const bool defer_sig = ctx->use_side && !ctx->serial_tail && n >= defer_min && !scalars && total_n / nchunks >= 2048;
+    if (!defer_sig) {
+        if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));   // join: pair number n is in place
+        return run_miller(ctx, n + 1, slot);
+    }
+    rc = run_miller(ctx, n, slot);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));
+    // the events of the big loop must survive for the stage report: run the one-pair loop with its own event window
+    cudaEvent_t saved[8];
+    const int ids[4] = {ST_LINES, ST_ACC, ST_GTPROD, ST_PARTIAL};
+    for (int k = 0; k < 4; k++) { saved[2 * k] = ctx->ev[2 * ids[k]]; saved[2 * k + 1] = ctx->ev[2 * ids[k] + 1]; }
+    for (int k = 0; k < 4; k++) { ctx->ev[2 * ids[k]] = ctx->ev_scratch[2 * k]; ctx->ev[2 * ids[k] + 1] = ctx->ev_scratch[2 * k + 1]; }
+    rc = run_miller(ctx, 1, slot + 1, n);
+    for (int k = 0; k < 4; k++) { ctx->ev[2 * ids[k]] = saved[2 * k]; ctx->ev[2 * ids[k] + 1] = saved[2 * k + 1]; }
+    if (rc) return rc;
+    blsgpu_ctx::dev_prog p2;
+    rc = get_prog(ctx, 4, 2, p2);
+    if (rc) return rc;
+    // in place: the program loads all 24 inputs into its slot file before the first round and stores at the end
+    rc = launch_prog(ctx, p2, (const fp *)(ctx->d_partials + slot), (fp *)(ctx->d_partials + slot));
+    if (rc) return rc;
+    END(ST_PARTIAL, s);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_inf, const fp12 *d_partials = nullptr,
@@ -814,6 +860,7 @@ extern "C" int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_dev
     int f[4];
     memcpy(f, ctx->h_pinned + 576, sizeof f);
     if (flags) *flags = f[0];
+    if (f[0]) memset(partial_out, 0, 576);                  // sealed like blsgpu_partial_dev: zero absorbs the product
     return 0;
 }
 
@@ -834,7 +881,8 @@ extern "C" int blsgpu_partial_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n,
     int rc = run_partial(ctx, (const sigset *)d_sets, n, first, total_n, srb, chunks, nullptr, 0);
     if (rc) return rc;
     CK(cudaMemcpyAsync(d_partial_out, ctx->d_partials, 576, cudaMemcpyDeviceToDevice, s));
-    if (d_flag_out) { k_copy_flag<<<1, 32, 0, s>>>(ctx->d_flags, d_flag_out); ctx->launches++; }
+    k_partial_seal<<<1, 32, 0, s>>>(ctx->d_flags, (uint32_t *)d_partial_out, d_flag_out);
+    ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }

@@ -574,8 +574,14 @@ __global__ void k_partial_one(fp12 *out, int *flag_out) {
     *out = one;
     if (flag_out) *flag_out = 0;
 }
-__global__ void k_copy_flag(const int *src, int *dst) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *dst = *src;
+// Seal a rank partial: a share that saw an infinite public key (flag set, aggregate.c:296) emits the ZERO element of
+// Fp12 instead of its Miller value.  Zero absorbs the product of the gathered partials and the final exponentiation maps
+// it to zero, which is not one: the batch is rejected with an all-zero GT by whoever finalises, so the 576-byte partial
+// is the only thing ranks have to exchange (one collective).  The flag is still copied out for callers that want it.
+__global__ void k_partial_seal(const int *flags, uint32_t *partial, int *flag_out) {
+    const int f = flags[0];
+    if (flag_out && threadIdx.x == 0) *flag_out = f;
+    if (f) for (int w = threadIdx.x; w < 144; w += blockDim.x) partial[w] = 0u;
 }
 
 // ---- warp-cooperative tail: interpreter for the Fp dataflow programs compiled by fpprog.hpp ----
@@ -595,9 +601,11 @@ __device__ __forceinline__ void fp_program_body(const uint32_t *prog, const fp *
     extern __shared__ uint4 sm4[];
     fp *slots = (fp *)sm4;
     const int lane = threadIdx.x;
-    in0 += (size_t)blockIdx.x * s_in0;
-    if (in1) in1 += (size_t)blockIdx.x * s_in1;
-    out0 += (size_t)blockIdx.x * s_out;
+    if (s_in0 != ~(size_t)0) {                             // ~0: the caller has positioned the pointers (k_fp_program_rows)
+        in0 += (size_t)blockIdx.x * s_in0;
+        if (in1) in1 += (size_t)blockIdx.x * s_in1;
+        out0 += (size_t)blockIdx.x * s_out;
+    }
     const uint32_t nr = prog[0], nin = prog[2], nout = prog[3];
     if (lane == 0) fp_set_zero(slots[0]);
     for (uint32_t e = lane; e < nin; e += 32) {
@@ -648,6 +656,14 @@ __global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const f
 __global__ void __launch_bounds__(32) k_fp_program_stream(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst,
                                                           fp *out0, size_t s_in0, size_t s_in1, size_t s_out) {
     fp_program_body<true>(prog, in0, in1, cst, out0, s_in0, s_in1, s_out);
+}
+
+// Row-wise instances for the product trees of the GT product: block b = (row j, group g) of m groups per row reads the 8
+// Fp12 values in[j * in_stride + 8 g ..] and writes one to out[j * out_stride + g] (strides in Fp12 values).
+__global__ void __launch_bounds__(32) k_fp_program_rows(const uint32_t *prog, const fp *in, const fp *cst, fp *out, unsigned m,
+                                                        size_t in_stride, size_t out_stride) {
+    const size_t j = blockIdx.x / m, g = blockIdx.x % m;
+    fp_program_body<false>(prog, in + (j * in_stride + 8 * g) * 12, nullptr, cst, out + (j * out_stride + g) * 12, ~(size_t)0, 0, 0);
 }
 
 // the Fp inversion lifted out of the final-exponentiation program (fpprog.hpp INV_EXTERNAL): one thread, binary Euclid

@@ -57,6 +57,14 @@ def make_sets(start_seed, n, msg_prefix=b"msg", threads=0):
     return bytes(out)
 
 
+def make_sets_device_recipe(seed, first, n, threads=0):
+    """The bytes blsgpu_make_sets(seed, first, n) generates on the device, computed with BLST on the host cores (the
+    benchmark workload for the reference arm; equality with the device generator is a GPU test)."""
+    out = _out(320 * n)
+    ref.ref_make_sets_device_recipe(C.c_uint64(seed), C.c_size_t(first), C.c_size_t(n), out, C.c_int(threads))
+    return bytes(out)
+
+
 def make_set(seed, message):
     """One set with an explicit message string (hashed with SHA-256 first)."""
     out = _out(320)

@@ -262,6 +262,41 @@ void ref_make_sets(uint64_t start, size_t n, const uint8_t *prefix, size_t plen,
     run_split(gen_thread, jobs, sizeof(gen_job), n, threads, gen_setrange);
 }
 
+/* The benchmark workload, on the host: the same bytes blsgpu_make_sets generates on the device (include/blsgpu.h:
+   sk_i = 1-or'ed (SHA256(LE64(seed) || 0^24 || LE64(first+i)) read as a big-endian integer, mod 2^250),
+   pk = [sk]G1, msg = SHA256("blsgpu" || LE64(first+i)), sig = [sk]H(msg)), so that the reference arm of bench.py can
+   verify the first n sets of the SAME workload without a GPU.  blst_scalar is 32 little-endian bytes (blst.h:61). */
+typedef struct { uint64_t seed; size_t first, lo, hi; uint8_t *out; } dgen_job;
+static void *dgen_thread(void *p) {
+    dgen_job *j = p;
+    for (size_t i = j->lo; i < j->hi; i++) {
+        uint64_t idx = j->first + i;
+        uint8_t pre[40] = {0}, dig[32], m14[14] = {'b', 'l', 's', 'g', 'p', 'u'}, msg[32];
+        for (int k = 0; k < 8; k++) { pre[k] = (uint8_t)(j->seed >> (8 * k)); pre[32 + k] = (uint8_t)(idx >> (8 * k)); m14[6 + k] = (uint8_t)(idx >> (8 * k)); }
+        blst_sha256(dig, pre, 40);
+        blst_scalar sk;
+        for (int k = 0; k < 32; k++) sk.b[k] = dig[31 - k];
+        sk.b[31] &= 0x03;
+        sk.b[0] |= 1;
+        blst_sha256(msg, m14, 14);
+        uint8_t *out = j->out + 320 * i;
+        blst_p1 pk; blst_p2 h;
+        blst_sk_to_pk_in_g1(&pk, &sk);
+        blst_p1_to_affine((blst_p1_affine *)out, &pk);
+        memcpy(out + 96, msg, 32);
+        blst_hash_to_g2(&h, msg, 32, (const uint8_t *)DST, DST_LEN, NULL, 0);
+        blst_sign_pk_in_g1(&h, &h, &sk);
+        blst_p2_to_affine((blst_p2_affine *)(out + 128), &h);
+    }
+    return NULL;
+}
+static void dgen_setrange(void *j, size_t lo, size_t hi) { ((dgen_job *)j)->lo = lo; ((dgen_job *)j)->hi = hi; }
+void ref_make_sets_device_recipe(uint64_t seed, size_t first, size_t n, uint8_t *out, int threads) {
+    dgen_job jobs[256];
+    for (int t = 0; t < 256; t++) { jobs[t].seed = seed; jobs[t].first = first; jobs[t].out = out; }
+    run_split(dgen_thread, jobs, sizeof(dgen_job), n, threads, dgen_setrange);
+}
+
 /* committee of nkeys signers on one message: aggregate pubkey + aggregate signature as ONE set
    (bls_batch_verifier.nim:38-40; fastAggregateVerify caller pattern bls_sig_min_pubkey.nim:234-258) */
 int ref_aggregate_g1(const uint8_t *pts, size_t n, uint8_t out[96]);

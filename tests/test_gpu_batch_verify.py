@@ -28,6 +28,21 @@ def test_valid_batches(cache, br, srb, n, chunks):
 
 
 @pytest.mark.parametrize("chunks", [0, 4])
+def test_config0_64_sets(cache, br, srb, chunks):
+    """BASELINE configs[0] exactly: 64 distinct-message sets (sk_i from ikm LE64(i),
+    m_i = SHA256("msg" || dec(i)), srb = SHA256("Mr F was here")), serial and 4-chunk derivations, plus the two negative
+    variants of tests/t_batch_verifier.nim at that size: one wrong signature (:122-137) and one forged pair (:198-244)."""
+    sets = examples(br, 64)
+    assert both(cache, br, sets, srb, chunks) is True
+    wrong = bytearray(sets)
+    wrong[17 * 320 + 128:18 * 320] = sets[40 * 320 + 128:41 * 320]      # (pubkey17, msg17, sig40)
+    assert both(cache, br, bytes(wrong), srb, chunks) is False
+    forged = sets[:62 * 320] + forged_pair(br, cache, 3, b"msg300", 4, b"msg400")
+    assert len(forged) == 64 * 320
+    assert both(cache, br, forged, srb, chunks) is False
+
+
+@pytest.mark.parametrize("chunks", [0, 4])
 def test_wrong_signature(cache, br, srb, chunks):
     s1 = br.make_set(1, b"msg1")
     s2 = br.make_set(2, b"msg2")

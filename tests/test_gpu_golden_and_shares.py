@@ -69,7 +69,47 @@ def test_rank_shares_on_one_device(cache, br, srb, world):
     p, f = be.partial(b"", 0, 21, srb, 4)
     assert be.finalize(p) == (True, br.finalize(br.partial(b"", 0, 21, srb, 4)[0])[1])
     inf = bytes(96) + sets[96:320]
-    assert be.partial(inf, 0, 1, srb, 0)[1] != 0
+    p_inf, f_inf = be.partial(inf, 0, 1, srb, 0)
+    assert f_inf != 0
+    # ... and the flagged share's partial is sealed: zero absorbs the product, the final exponentiation keeps it zero,
+    # so the 576 bytes alone carry the verdict (bls_batch_verifier.nim:153: update() false -> batch false)
+    assert p_inf == bytes(576)
+    good = be.partial(sets[:320 * 5], 0, 5, srb, 0)[0]
+    assert be.finalize(good + p_inf) == (False, bytes(576))
+
+
+def test_deferred_signature_pair_vs_blst(br, srb):
+    """Large batch behind long scalar chains (the drop-in's tp.numThreads = 4 chunks of 4 100 sets): the n set pairs run
+    their multi-Miller loop without waiting for the signature-side MSM, pair number n = (S, -G1) gets its own loop and
+    the two values are multiplied (blsgpu.cu run_partial).  Verdict and GT must equal BLST's."""
+    import nim_blscurve_b200 as bg
+    n = 16400
+    big = bg.BatchedBLSVerifierCache(max_sets=n, device=0)
+    try:
+        out = (C.c_uint8 * (320 * n))()
+        assert bg.lib().blsgpu_make_sets(big.handle, 5, 0, n, out, 0) == 0
+        sets = bytes(out)
+        assert big.verify_raw(sets, srb, 4) is True
+        bad = bytearray(sets)
+        bad[9999 * 320 + 100] ^= 0x04
+        got = big.verify_raw(bytes(bad), srb, 4, want_gt=True)
+        assert got[0] is False
+        assert got == br.batch_verify(bytes(bad), srb, 4)
+        # the serial derivation (one chain of 16 400) takes the same route
+        assert big.verify_raw(bytes(bad), srb, 0, want_gt=True) == br.batch_verify(bytes(bad), srb, 0)
+    finally:
+        big.close()
+
+
+def test_device_generated_sets_equal_blst_recipe(cache, br):
+    """The benchmark workload generator (k_make_sets: the device's own hash_to_G2 and scalar multiplications) against
+    the same recipe computed with BLST on the host (oracle ref_make_sets_device_recipe): byte-identical sets, so the
+    batches bench.py times are the ones the reference arm verifies."""
+    import nim_blscurve_b200 as bg
+    n = 300
+    out = (C.c_uint8 * (320 * n))()
+    assert bg.lib().blsgpu_make_sets(cache.handle, 2026, 1000, n, out, 0) == 0
+    assert bytes(out) == br.make_sets_device_recipe(2026, 1000, n)
 
 
 def test_large_batch_properties(cache, br, srb):

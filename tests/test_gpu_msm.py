@@ -177,3 +177,22 @@ def test_msm_rank_shares_on_one_device(cache, br, world):
             f, c = bg.shard_range(n, world, r)
             parts += bg.msm_g1_distributed(be, pts[f * 96:(f + c) * 96], sc[f * 32:(f + c) * 32], 255)   # world-1 path
         assert be.aggregate_g1(parts) == br.msm_g1(pts, sc, 255)
+
+
+def test_msm_g1_2pow22_slice_sum(cache, br):
+    """BASELINE configs[2] at its largest size, 2^22 points (c = 19 in the reference's window rule,
+    multi_scalar.c:275-289): the MSM over the whole range equals the aggregateAll of the MSMs over five unequal slices
+    (2^21, 2^20, 2^19 and two odd sizes: different window shapes), and the last slice — small enough for the oracle —
+    is pinned against blst_p1s_mult_pippenger."""
+    import nim_blscurve_b200 as bg
+    n = 1 << 22
+    dp, ds = _device_msm_inputs(cache, n, 0x2222)
+    whole = _msm_dev(cache, dp, ds, n)
+    cuts = [0, 1 << 21, (1 << 21) + (1 << 20), (1 << 21) + (1 << 20) + (1 << 19), n - 50021, n]
+    parts = [_msm_dev(cache, dp, ds, cuts[i + 1] - cuts[i], cuts[i]) for i in range(5)]
+    ok, total = bg.aggregateAll(cache, parts)
+    assert ok and total == whole
+    lo, cnt = cuts[4], cuts[5] - cuts[4]
+    pts = dp[96 * lo:96 * (lo + cnt)].cpu().numpy().tobytes()
+    sc = ds[32 * lo:32 * (lo + cnt)].cpu().numpy().tobytes()
+    assert parts[4] == br.msm_g1(pts, sc, 255)
