@@ -563,9 +563,17 @@ def main():
             cblk = (C.c_uint8 * (blk * 320)).from_buffer_copy(sets_host[:blk * 320])
             tbh, rch = wall(lambda: L.blsgpu_batch_verify(h, cblk, blk, srb, 4, None, gt), 5)
             extra["block_batch"]["ms_from_host_buffer"] = tbh * 1e3
+            # stage breakdown: event timing does not exist inside a replayed CUDA graph, so a second context with graphs off
+            os.environ["BLSGPU_GRAPH"] = "0"
+            c_ng = bg.BatchedBLSVerifierCache(max_sets=blk, device=local)
+            del os.environ["BLSGPU_GRAPH"]
+            tng, _ = wall(lambda: L.blsgpu_batch_verify(c_ng.handle, cblk, blk, srb, 4, None, gt), 5)
             ms_ = (C.c_float * 16)()
-            kk = L.blsgpu_last_stage_ms(h, ms_, 16)
+            kk = L.blsgpu_last_stage_ms(c_ng.handle, ms_, 16)
             extra["block_batch"]["stages_ms"] = {L.blsgpu_stage_name(i).decode(): ms_[i] for i in range(kk)}
+            extra["block_batch"]["ms_without_cuda_graph"] = tng * 1e3
+            extra["block_batch"]["launches_without_cuda_graph"] = L.blsgpu_last_launches(c_ng.handle)
+            c_ng.close()
             # the same block with the public-key aggregation done on the GPU first: 128 committees x 128 keys + one of 512
             nkeys = min(128 * 128 + 512, (S // 129) * 129)
             member = bytes(h_sets[:nkeys * 320].numpy().reshape(nkeys, 320)[:, :96].tobytes())

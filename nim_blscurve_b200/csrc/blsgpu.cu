@@ -69,6 +69,13 @@ struct blsgpu_ctx {
     fp12 *d_gt = nullptr;                                    // final exponentiation result, Montgomery form
     bool serial_tail = false;
     bool prog_smem_raised = false;                           // k_fp_program allowed > 48 KiB of shared memory on this device
+    // host-buffer calls on large batches: the H2D copy is cut into H2D_SLICES pieces on a copy stream and the hash kernel
+    // into as many launches on their own streams, each waiting for its piece only (run_partial_impl)
+    const uint8_t *h_src = nullptr;                          // caller's host buffer for the current call (borrowed)
+    cudaStream_t copy_stream = nullptr, slice_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copy[4], ev_slice[4];
+    bool slices_ready = false;
+    bool chain_smem_raised = false;                          // k_rlc_scalars allowed to reserve a whole SM's shared memory
     // multi-device context (blsgpu_create_multi): this context is the leader (share 0 + the one final exponentiation),
     // peers[k-1] owns share k on its own device; the 576-byte partials and the flags are gathered into the leader
     std::vector<blsgpu_ctx *> peers;
@@ -76,6 +83,15 @@ struct blsgpu_ctx {
     int *d_gather_flags = nullptr;                           // ndev infinite-public-key flags
     cudaEvent_t ev_share = nullptr;                          // "this share's partial is ready" (recorded on the share's stream)
     size_t multi_cap = 0;                                    // capacity of the whole multi-device context (leader only)
+    // CUDA graphs for the small-batch route: a block-sized batch is ~35 launches on three streams, i.e. ~40 driver calls
+    // per batch from the host thread; the second call with the same (sets pointer, n, chunks) captures the whole
+    // sequence (fork / join included) and every later one replays it with ONE launch.  The 32 random bytes reach the
+    // scalar kernel through device memory (d_srb), refreshed by a copy node from a fixed pinned address.
+    struct graph_entry { const void *sets; size_t n; uint32_t chunks; int seen; cudaGraphExec_t exec; };
+    std::vector<graph_entry> graphs;
+    bool use_graph = true;
+    bool srb_from_dev = false;                               // launch_scalars: read the random bytes from d_srb
+    uint32_t *d_srb = nullptr;
     std::string err;
 };
 
@@ -111,8 +127,13 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     for (blsgpu_ctx *p : ctx->peers) blsgpu_destroy(p);
     ctx->peers.clear();
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_gather); cudaFree(ctx->d_gather_flags);
+    cudaFree(ctx->d_gather); cudaFree(ctx->d_gather_flags); cudaFree(ctx->d_srb);
+    for (auto &g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->ev_share) cudaEventDestroy(ctx->ev_share);
+    if (ctx->slices_ready) {
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int k = 0; k < 4; k++) { cudaStreamDestroy(ctx->slice_stream[k]); cudaEventDestroy(ctx->ev_copy[k]); cudaEventDestroy(ctx->ev_slice[k]); }
+    }
     if (ctx->ev_scratch_valid) for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev_scratch[i]);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_r); cudaFree(ctx->d_H); cudaFree(ctx->d_Pj); cudaFree(ctx->d_Q);
     cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gtb);
@@ -175,6 +196,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     ALLOC(ctx->d_consts, fpprog::CONST_COUNT * sizeof(fp));
     ALLOC(ctx->d_norm, 2 * sizeof(fp));
     ALLOC(ctx->d_flags, 4 * sizeof(int));
+    ALLOC(ctx->d_srb, 32);
 #undef ALLOC
     if ((e = cudaMallocHost((void **)&ctx->h_pinned, 4096)) != cudaSuccess) return bad("cudaMallocHost", e);
     if ((e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB1, FROB1, sizeof(FROB1), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
@@ -196,6 +218,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
     if (getenv("BLSGPU_SIDE_STREAM")) ctx->use_side = atoi(getenv("BLSGPU_SIDE_STREAM")) != 0;
+    if (getenv("BLSGPU_GRAPH")) ctx->use_graph = atoi(getenv("BLSGPU_GRAPH")) != 0;
     if ((e = cudaEventCreateWithFlags(&ctx->ev_share, cudaEventDisableTiming)) != cudaSuccess) return bad("cudaEventCreate", e);
     for (int i = 0; i < 8; i++) if ((e = cudaEventCreate(&ctx->ev_scratch[i])) != cudaSuccess) return bad("cudaEventCreate", e);
     ctx->ev_scratch_valid = true;
@@ -282,7 +305,26 @@ static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size
     }
     if (!srb) return fail(ctx, BLSGPU_ERR_ARG, "secureRandomBytes is NULL");
     size_t nb = chunks == 0 ? 1 : (total_n < chunks ? total_n : (size_t)chunks);
-    k_rlc_scalars<<<nblk(nb, 64), 64, 0, s>>>(words_of(srb), total_n, chunks, first, n, ctx->d_r);
+    // Long chains (thousands of sequential SHA-256 blocks per reference chunk) are pure single-warp latency, and every
+    // consumer of the scalars waits for them.  Sharing an SM with the hash kernel's 16 warps costs the chain warp half
+    // of its issue slots (measured: 24-31 ms instead of 13 ms for 8 192 blocks per chain), so a block of chains asks for
+    // the whole shared memory of an SM and therefore gets one to itself: 32 chains per block, one SM per 32 chunks.
+    size_t hog = 0;
+    static const size_t hog_min = getenv("BLSGPU_CHAIN_HOG_MIN") ? (size_t)atoll(getenv("BLSGPU_CHAIN_HOG_MIN")) : 1024;
+    if (total_n / nb >= hog_min) {
+        hog = 227 * 1024;
+        if (!ctx->chain_smem_raised) {
+            CK(cudaFuncSetAttribute(k_rlc_scalars, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hog));
+            ctx->chain_smem_raised = true;
+        }
+    }
+    if (ctx->srb_from_dev) {
+        // h_pinned + 1024: 8 big-endian words written by the caller of the captured sequence before every launch
+        CK(cudaMemcpyAsync(ctx->d_srb, ctx->h_pinned + 1024, 32, cudaMemcpyHostToDevice, s));
+        k_rlc_scalars<<<nblk(nb, 32), 32, hog, s>>>(words8(), ctx->d_srb, total_n, chunks, first, n, ctx->d_r);
+    } else {
+        k_rlc_scalars<<<nblk(nb, 32), 32, hog, s>>>(words_of(srb), nullptr, total_n, chunks, first, n, ctx->d_r);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -357,6 +399,11 @@ static size_t small_lines_max() {
     return v > 16385 ? 16385 : v;
 }
 #define SMALL_ROUTE_MAX SMALL_ROUTE_CAP   /* buffer strides */
+// Mid-size route: two lanes per set for H(m_i) and the line evaluations (fp2h.cuh) while a thread per set leaves the
+// machine under-filled: 148 SMs x 512 resident threads = 75 776 lanes, i.e. up to ~38k sets in one wave of lane pairs.
+static size_t pair_hash_min() { static const size_t v = getenv("BLSGPU_PAIR_HASH_MIN") ? (size_t)atoll(getenv("BLSGPU_PAIR_HASH_MIN")) : 1025; return v; }
+static size_t pair_hash_max() { static const size_t v = getenv("BLSGPU_PAIR_HASH_MAX") ? (size_t)atoll(getenv("BLSGPU_PAIR_HASH_MAX")) : 40000; return v; }
+static size_t pair_lines_max() { static const size_t v = getenv("BLSGPU_PAIR_LINES_MAX") ? (size_t)atoll(getenv("BLSGPU_PAIR_LINES_MAX")) : 40000; return v; }
 #define SMALL_FP_PER_SET (6 + 6 + 6 + 6 + 64)
 
 // Work decomposition of the accumulation: G pairs per group (they share the Fp12 squarings) and nseg loop segments,
@@ -444,6 +491,8 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot, size_t pair0 = 0) {
             k_lines_from_prog<<<nblk(t * ML_NLINES * ML_LINE_WORDS, 256), 256, 0, s>>>((const uint32_t *)ctx->d_small_lines, ctx->d_Q + pair0, ctx->d_P + pair0, t,
                                                                                       ctx->d_lines, stride);
             ctx->launches++;
+        } else if (t <= pair_lines_max()) {
+            k_miller_lines_lanes2<<<nblk(2 * t), 128, 0, s>>>(ctx->d_Q + pair0 + off, ctx->d_P + pair0 + off, t, ctx->d_lines, stride);
         } else {
             k_miller_lines<<<nblk(t), 128, 0, s>>>(ctx->d_Q + pair0 + off, ctx->d_P + pair0 + off, t, ctx->d_lines, stride);
         }
@@ -526,6 +575,10 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
     if (rc) {
         cudaStreamSynchronize(ctx->side);
         cudaStreamSynchronize(ctx->side2);
+        if (ctx->slices_ready) {
+            cudaStreamSynchronize(ctx->copy_stream);
+            for (int k = 0; k < 4; k++) cudaStreamSynchronize(ctx->slice_stream[k]);
+        }
         cudaStreamSynchronize(ctx->stream);
         cudaGetLastError();
     }
@@ -536,6 +589,23 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     cudaStream_t s = ctx->stream;
     ctx->launches = 0;
     if (!scalars && !srb) return fail(ctx, BLSGPU_ERR_ARG, "secureRandomBytes is NULL");
+    // Host-buffer call (blsgpu_batch_verify): this function issues the H2D copy itself.  Small and mid-size batches: one
+    // copy ahead of everything.  Large ones: H2D_SLICES pieces on a copy stream, each followed at once by the launch of
+    // the hash kernel over that piece on its own stream, so the copy (and, for pageable memory, the host-side staging
+    // that blocks the calling thread piece by piece) hides behind H(m_i) of the earlier pieces.
+    enum { H2D_SLICES = 4 };
+    static const size_t slice_min = getenv("BLSGPU_H2D_SLICE_MIN") ? (size_t)atoll(getenv("BLSGPU_H2D_SLICE_MIN")) : 32768;
+    const bool sliced = ctx->h_src && (const void *)d_sets == (const void *)ctx->d_sets && n >= slice_min && n > small_route_max();
+    if (ctx->h_src && !sliced) CK(cudaMemcpyAsync(ctx->d_sets, ctx->h_src, n * sizeof(sigset), cudaMemcpyHostToDevice, s));
+    if (sliced && !ctx->slices_ready) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < H2D_SLICES; k++) {
+            CK(cudaStreamCreateWithFlags(&ctx->slice_stream[k], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->ev_copy[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_slice[k], cudaEventDisableTiming));
+        }
+        ctx->slices_ready = true;
+    }
     CK(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
     // fork: the scalar chain (strictly sequential SHA-256 per reference chunk: tens of milliseconds for a large batch
     // when the caller passes tp.numThreads = 16..32 chunks) and the signature-side sum that consumes the scalars run on
@@ -565,7 +635,8 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     // programs, one warp per set (fpprog.hpp build_g2_clear_cofactor / build_g2_mul64)
     static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 15;   // bit 0 hash, bit 1 sig (bit 2: lines, bit 3: GT product, run_miller)
     const bool small = small_env != 0 && n <= small_route_max() && !ctx->serial_tail;
-    const bool small_hash = small && (small_env & 1), small_sig = small && (small_env & 2);
+    const bool pair_hash = n >= pair_hash_min() && n <= pair_hash_max();
+    const bool small_hash = small && (small_env & 1) && !pair_hash, small_sig = small && (small_env & 2);
     blsgpu_ctx::dev_prog p_cof, p_mul;
     fp *sm_hash_in = nullptr, *sm_hash_out = nullptr, *sm_sig_in = nullptr, *sm_sig_out = nullptr, *sm_bits = nullptr;
     if (small) {
@@ -578,6 +649,29 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
         sm_sig_in = sm_hash_out + 6 * SMALL_ROUTE_MAX;
         sm_sig_out = sm_sig_in + 6 * SMALL_ROUTE_MAX;
         sm_bits = sm_sig_out + 6 * SMALL_ROUTE_MAX;
+    }
+    if (sliced) {
+        if (!ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_FORK], s));
+        BEGIN(ST_HASH, s);
+        const size_t per = ((n + H2D_SLICES - 1) / H2D_SLICES + 127) & ~(size_t)127;      // whole thread blocks per piece
+        for (int k = 0; k < H2D_SLICES; k++) {
+            const size_t off = (size_t)k * per;
+            if (off >= n) { CK(cudaEventRecord(ctx->ev_copy[k], ctx->copy_stream)); CK(cudaEventRecord(ctx->ev_slice[k], ctx->copy_stream)); continue; }
+            const size_t len = n - off < per ? n - off : per;
+            if (k == 0) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[EV_FORK], 0));     // after whatever preceded on s
+            CK(cudaMemcpyAsync(ctx->d_sets + off, ctx->h_src + off * sizeof(sigset), len * sizeof(sigset), cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_copy[k], ctx->copy_stream));
+            cudaStream_t sk = ctx->slice_stream[k];
+            CK(cudaStreamWaitEvent(sk, ctx->ev_copy[k], 0));
+            if (pair_hash) k_hash_sets_lanes2<<<nblk(2 * len), 128, 0, sk>>>(d_sets + off, len, ctx->d_H + off);
+            else k_hash_sets<<<nblk(len), 128, 0, sk>>>(d_sets + off, len, ctx->d_H + off);
+            ctx->launches++;
+            CK(cudaEventRecord(ctx->ev_slice[k], sk));
+        }
+        for (int k = 0; k < H2D_SLICES; k++) CK(cudaStreamWaitEvent(s, ctx->ev_slice[k], 0));
+        END(ST_HASH, s);
+        CK(cudaStreamWaitEvent(g, ctx->ev_copy[H2D_SLICES - 1], 0));    // the signature-side MSM reads every set
     }
     BEGIN(ST_G2MUL, g);
     // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
@@ -613,15 +707,18 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     ctx->launches++;
     END(ST_G2SUM, g);
     if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_JOIN], g));
-    BEGIN(ST_HASH, s);
-    if (small_hash) {
+    if (!sliced) BEGIN(ST_HASH, s);
+    if (sliced) {
+        // hashed piece by piece above
+    } else if (small_hash) {
         k_hash_map_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, sm_hash_in);
         launch_prog_many(ctx, p_cof, s, n, sm_hash_in, 6, nullptr, 0, sm_hash_out, 6);
         k_g2_hom_to_jac<<<nblk(n), 128, 0, s>>>(sm_hash_out, n, ctx->d_H);
         ctx->launches += 2;
-    } else if (n <= 8192) k_hash_sets_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+    } else if (pair_hash) k_hash_sets_lanes2<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+    else if (n <= 8192) k_hash_sets_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
     else k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
-    END(ST_HASH, s);
+    if (!sliced) END(ST_HASH, s);
     if (g1_aside) {
         CK(cudaStreamWaitEvent(s, ctx->ev[EV_G1], 0));
     } else {
@@ -670,8 +767,8 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     return 0;
 }
 
-static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_inf, const fp12 *d_partials = nullptr,
-                     const int *d_rank_flags = nullptr) {
+// enqueue: product of the partials, final exponentiation, verdict + GT bytes, and their copies into h_pinned
+static int run_final_enqueue(blsgpu_ctx *ctx, int count, const fp12 *d_partials = nullptr, const int *d_rank_flags = nullptr) {
     cudaStream_t s = ctx->stream;
     const fp12 *parts = d_partials ? d_partials : ctx->d_partials;
     BEGIN(ST_FINAL, s);
@@ -696,14 +793,24 @@ static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_in
     END(ST_FINAL, s);
     CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_gtb, 576, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_pinned + 576, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+// wait and read the verdict
+static int run_final_finish(blsgpu_ctx *ctx, uint8_t gt_out[576], int *pk_inf, bool rank_flags) {
+    CK(cudaStreamSynchronize(ctx->stream));
     int flags[4];
     memcpy(flags, ctx->h_pinned + 576, sizeof flags);
     // the gathered per-share flags when the caller supplies them (finalize_dev), else this context's own flag from the
     // run_partial that preceded (batch_verify_dev); never both: d_flags[0] may be stale from an earlier, unrelated batch
-    if (pk_inf) *pk_inf = d_rank_flags ? flags[2] : flags[0];
+    if (pk_inf) *pk_inf = rank_flags ? flags[2] : flags[0];
     if (gt_out) memcpy(gt_out, ctx->h_pinned, 576);
     return flags[1] ? 1 : 0;
+}
+static int run_final(blsgpu_ctx *ctx, int count, uint8_t gt_out[576], int *pk_inf, const fp12 *d_partials = nullptr,
+                     const int *d_rank_flags = nullptr) {
+    int rc = run_final_enqueue(ctx, count, d_partials, d_rank_flags);
+    if (rc) return rc;
+    return run_final_finish(ctx, gt_out, pk_inf, d_rank_flags != nullptr);
 }
 
 static void collect_stage_times(blsgpu_ctx *ctx, bool with_final) {
@@ -727,17 +834,77 @@ extern "C" int blsgpu_rlc_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t
     return 0;
 }
 
+// Small batches through a CUDA graph.  First call with a key: direct launches (all lazy allocations and program uploads
+// happen there).  Second call: the same sequence under stream capture (the fork to the side streams and the joins are
+// captured with it), instantiated and launched.  Later calls: one cudaGraphLaunch.  `done` = the work of this call is
+// queued and the caller only has to wait for it; done == false (first sighting, or capture unsupported) = run directly.
+static int verify_graphed(blsgpu_ctx *ctx, const void *d_sets, size_t n, const uint8_t srb[32], uint32_t chunks, bool &done) {
+    done = false;
+    blsgpu_ctx::graph_entry *e = nullptr;
+    for (auto &g : ctx->graphs) if (g.sets == d_sets && g.n == n && g.chunks == chunks) { e = &g; break; }
+    if (!e) {
+        if (ctx->graphs.size() >= 16) {                      // bounded cache: drop the oldest entry
+            if (ctx->graphs.front().exec) cudaGraphExecDestroy(ctx->graphs.front().exec);
+            ctx->graphs.erase(ctx->graphs.begin());
+        }
+        ctx->graphs.push_back({d_sets, n, chunks, 1, nullptr});
+        return 0;
+    }
+    const words8 w = words_of(srb);
+    memcpy(ctx->h_pinned + 1024, w.w, 32);                   // no copy is in flight: every call on a context ends with a sync
+    if (!e->exec) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->use_graph = false;
+            return 0;
+        }
+        ctx->srb_from_dev = true;
+        int rc = run_partial_impl(ctx, (const sigset *)d_sets, n, 0, n, srb, chunks, nullptr, 0);
+        if (!rc) rc = run_final_enqueue(ctx, 1);
+        ctx->srb_from_dev = false;
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc || ce != cudaSuccess || !graph) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            ctx->use_graph = false;                          // run directly from now on (and for this call)
+            return 0;
+        }
+        ce = cudaGraphInstantiate(&e->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { cudaGetLastError(); e->exec = nullptr; ctx->use_graph = false; return 0; }
+    }
+    CK(cudaGraphLaunch(e->exec, ctx->stream));
+    ctx->launches = 1;
+    done = true;
+    return 0;
+}
+
 extern "C" int blsgpu_batch_verify_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n, const uint8_t srb[32],
                                        uint32_t chunks, const uint64_t *scalars, uint8_t gt_out[576]) {
     if (!ctx) return BLSGPU_ERR_ARG;
     if (gt_out) memset(gt_out, 0, 576);
     if (n == 0) return 0;                                   // bls_batch_verifier.nim:137, :312
     if (!d_sets) return fail(ctx, BLSGPU_ERR_ARG, "sets is NULL");
+    if ((uintptr_t)d_sets & 15) return fail(ctx, BLSGPU_ERR_ARG, "device sets pointer must be 16-byte aligned (TMA staging)");
     if (n > ctx->cap) return fail(ctx, BLSGPU_ERR_CAPACITY, "batch larger than context capacity");
     CK(cudaSetDevice(ctx->device));
-    int rc = run_partial(ctx, (const sigset *)d_sets, n, 0, n, srb, chunks, scalars, 0);
+    int rc, pk_inf = 0;
+    static const size_t graph_max = getenv("BLSGPU_GRAPH_MAX") ? (size_t)atoll(getenv("BLSGPU_GRAPH_MAX")) : 2047;
+    if (ctx->use_graph && !scalars && srb && n <= graph_max && !ctx->serial_tail) {
+        bool done = false;
+        rc = verify_graphed(ctx, d_sets, n, srb, chunks, done);
+        if (rc) return rc;
+        if (done) {
+            rc = run_final_finish(ctx, gt_out, &pk_inf, false);
+            for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;     // no event timing inside a graph (BLSGPU_GRAPH=0)
+            if (rc < 0) return rc;
+            if (pk_inf) { if (gt_out) memset(gt_out, 0, 576); return 0; }
+            return rc;
+        }
+    }
+    rc = run_partial(ctx, (const sigset *)d_sets, n, 0, n, srb, chunks, scalars, 0);
     if (rc) return rc;
-    int pk_inf = 0;
     rc = run_final(ctx, 1, gt_out, &pk_inf);
     collect_stage_times(ctx, true);
     if (rc < 0) return rc;
@@ -824,8 +991,16 @@ extern "C" int blsgpu_batch_verify(blsgpu_ctx *ctx, const void *sets, size_t n, 
     if (scalars)
         for (size_t i = 0; i < n; i++) if (scalars[i] == 0) return fail(ctx, BLSGPU_ERR_ARG, "explicit RLC scalar is zero");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->d_sets, sets, n * sizeof(sigset), cudaMemcpyHostToDevice, ctx->stream));
-    return blsgpu_batch_verify_dev(ctx, ctx->d_sets, n, srb, chunks, scalars, gt_out);
+    static const size_t graph_max = getenv("BLSGPU_GRAPH_MAX") ? (size_t)atoll(getenv("BLSGPU_GRAPH_MAX")) : 2047;
+    if (n <= graph_max) {
+        // small batches replay a captured graph that starts from ctx->d_sets: the copy stays outside of it
+        CK(cudaMemcpyAsync(ctx->d_sets, sets, n * sizeof(sigset), cudaMemcpyHostToDevice, ctx->stream));
+        return blsgpu_batch_verify_dev(ctx, ctx->d_sets, n, srb, chunks, scalars, gt_out);
+    }
+    ctx->h_src = (const uint8_t *)sets;                      // run_partial_impl issues the copy (whole, or in overlapped pieces)
+    int rc = blsgpu_batch_verify_dev(ctx, ctx->d_sets, n, srb, chunks, scalars, gt_out);
+    ctx->h_src = nullptr;
+    return rc;
 }
 
 extern "C" int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_device, size_t n, size_t first,
@@ -846,6 +1021,7 @@ extern "C" int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_dev
         return 0;
     }
     const sigset *d = (const sigset *)sets;
+    if (sets_on_device && ((uintptr_t)sets & 15)) return fail(ctx, BLSGPU_ERR_ARG, "device sets pointer must be 16-byte aligned (TMA staging)");
     if (!sets_on_device) {
         CK(cudaMemcpyAsync(ctx->d_sets, sets, n * sizeof(sigset), cudaMemcpyHostToDevice, s));
         d = ctx->d_sets;
@@ -878,6 +1054,7 @@ extern "C" int blsgpu_partial_dev(blsgpu_ctx *ctx, const void *d_sets, size_t n,
         return 0;
     }
     if (!d_sets) return fail(ctx, BLSGPU_ERR_ARG, "sets is NULL");
+    if ((uintptr_t)d_sets & 15) return fail(ctx, BLSGPU_ERR_ARG, "device sets pointer must be 16-byte aligned (TMA staging)");
     int rc = run_partial(ctx, (const sigset *)d_sets, n, first, total_n, srb, chunks, nullptr, 0);
     if (rc) return rc;
     CK(cudaMemcpyAsync(d_partial_out, ctx->d_partials, 576, cudaMemcpyDeviceToDevice, s));

@@ -17,6 +17,8 @@
 #include "pairing.cuh"
 #include "acc_team.cuh"
 #include "io.cuh"
+#include "pair_route.cuh"
+#include "tma_stage.cuh"
 
 namespace bls {
 
@@ -66,7 +68,11 @@ __device__ __forceinline__ void chunk_range(size_t nchunks, size_t total, size_t
 
 // One thread per reference chunk walks that chunk's sequential SHA-256 chain and stores the scalars of
 // the indices this rank owns ([first, first+n) of the global batch).
-__global__ void k_rlc_scalars(words8 srb, size_t total_n, uint32_t chunks, size_t first, size_t n, uint64_t *out) {
+// d_srb (nullable): the 32 random bytes as 8 big-endian words in device memory instead of the by-value copy — the
+// form a captured CUDA graph needs, where kernel arguments are frozen but the bytes change with every call.
+__global__ void k_rlc_scalars(words8 srb, const uint32_t *d_srb, size_t total_n, uint32_t chunks, size_t first, size_t n,
+                              uint64_t *out) {
+    if (d_srb) for (int k = 0; k < 8; k++) srb.w[k] = d_srb[k];
     size_t nb = chunks == 0 ? 1 : (total_n < chunks ? total_n : (size_t)chunks);
     size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nb) return;
@@ -123,11 +129,24 @@ __global__ void k_combine_scalars(words8 srb, size_t n, uint64_t *out) {
     }
 }
 
+// The 128 messages of the block (32 of the 320 bytes of each record) are staged into shared memory by TMA bulk copies
+// (tma_stage.cuh), 4 KB per block.
 __global__ void BLS_LB k_hash_sets(const sigset *sets, size_t n, g2_jac *H) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(128) uint8_t tile[128 * 32];
+    __shared__ uint64_t bar;
+    const size_t base = (size_t)blockIdx.x * blockDim.x;
+    const size_t cnt = n - base < blockDim.x ? n - base : blockDim.x;
+    tma_stage_rows(tile, 32, sets[base].msg, sizeof(sigset), (uint32_t)cnt, &bar);
+    size_t i = base + threadIdx.x;
     if (i >= n) return;
-    uint8_t msg[32], dst[43];
-    for (int k = 0; k < 32; k++) msg[k] = sets[i].msg[k];
+    alignas(16) uint8_t msg[32];
+    uint8_t dst[43];
+    {
+        const uint4 *m = (const uint4 *)(tile + 32 * threadIdx.x);
+        uint4 m0 = m[0], m1 = m[1];
+        *(uint4 *)msg = m0;
+        *(uint4 *)(msg + 16) = m1;
+    }
     for (int k = 0; k < 43; k++) dst[k] = DST_ETH2[k];
     g2_jac h;
     hash_to_g2_jac(h, msg, 32, dst, 43);
@@ -160,6 +179,46 @@ __global__ void BLS_LB k_hash_sets_pair(const sigset *sets, size_t n, g2_jac *H)
     g2_jac h;
     g2_clear_cofactor(h, q);
     H[i] = h;
+}
+
+// ---- mid-size route: two lanes per set (fp2h.cuh / pair_route.cuh) --------------------------------------------------
+// H(m_i) with every Fp2 operation split over a lane pair; lane pair t/2 owns set t/2.  Output identical to k_hash_sets.
+__global__ void BLS_LB k_hash_sets_lanes2(const sigset *sets, size_t n, g2_jac *H) {
+    __shared__ __align__(128) uint8_t tile[64 * 32];       // the block's 64 messages, TMA bulk copies (tma_stage.cuh)
+    __shared__ uint64_t bar;
+    const size_t base = (size_t)blockIdx.x * (blockDim.x >> 1);
+    const size_t cnt = n - base < (blockDim.x >> 1) ? n - base : (blockDim.x >> 1);
+    tma_stage_rows(tile, 32, sets[base].msg, sizeof(sigset), (uint32_t)cnt, &bar);
+    const size_t i = base + (threadIdx.x >> 1);
+    if (i >= n) return;                                    // both lanes of a pair leave together
+    alignas(16) uint8_t msg[32];
+    uint8_t dst[43];
+    {
+        const uint4 *m = (const uint4 *)(tile + 32 * (threadIdx.x >> 1));
+        *(uint4 *)msg = m[0];
+        *(uint4 *)(msg + 16) = m[1];
+    }
+    for (int k = 0; k < 43; k++) dst[k] = DST_ETH2[k];
+    g2h_jac h;
+    hash_to_g2_pair(h, msg, 32, dst, 43);
+    fp *out = (fp *)&H[i] + (h_odd() ? 1 : 0);             // g2_jac = x.c0 x.c1 y.c0 y.c1 z.c0 z.c1
+    out[0] = h.x.v;
+    out[2] = h.y.v;
+    out[4] = h.z.v;
+}
+// the 68 line triples of pair t/2, word for word those of k_miller_lines
+__global__ void __launch_bounds__(128, BLS_LB_BLOCKS) k_miller_lines_lanes2(const g2_aff *Q, const g1_aff *P, size_t np,
+                                                                            uint32_t *lines, size_t stride) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t p = t >> 1;
+    if (p >= np) return;
+    const fp *q = (const fp *)&Q[p] + (h_odd() ? 1 : 0);   // g2_aff = x.c0 x.c1 y.c0 y.c1
+    g2h_aff qh;
+    qh.x.v = q[0];
+    qh.y.v = q[2];
+    g1_aff a = P[p];
+    const bool inf = (f_is_zero(qh.x) & f_is_zero(qh.y)) | aff_is_inf(a);
+    miller_lines_pair(qh, a, inf, lines + p, stride);
 }
 
 // ---- small-batch route (<= 1024 sets): the long serial stretches run as per-set dataflow programs ----
@@ -266,9 +325,14 @@ __global__ void k_g2_mul_prep(const sigset *sets, const uint64_t *r, size_t n, f
 }
 
 __global__ void BLS_LB k_g1_mul(const sigset *sets, const uint64_t *r, size_t n, g1_jac *Pj, int *flags) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(128) sigset tile[128];            // the block's 128 sets, one TMA bulk copy (tma_stage.cuh)
+    __shared__ uint64_t bar;
+    const size_t base = (size_t)blockIdx.x * blockDim.x;
+    const size_t cnt = n - base < blockDim.x ? n - base : blockDim.x;
+    tma_stage_tile(tile, sets + base, (uint32_t)(cnt * sizeof(sigset)), &bar);
+    size_t i = base + threadIdx.x;
     if (i >= n) return;
-    g1_aff pk = sets[i].pk;
+    g1_aff pk = tile[threadIdx.x].pk;
     if (aff_is_inf(pk)) atomicOr(flags, 1);            // BLST_PK_IS_INFINITY (aggregate.c:296)
     g1_jac j;
     pt_mul_u64_w4(j, pk, r[i]);
