@@ -56,13 +56,20 @@ def host_threads():
     return os.cpu_count() or 1
 
 
+def default_chunks(world):
+    """RLC chunk count of the headline run = tp.numThreads of the caller: the host's hardware threads, and at least 16 per
+    GPU (a host that feeds N GPUs with N shares brings N x 16 threads' worth of chunks; the sequential SHA-256 chain of a
+    chunk — total/chunks blocks, ~2 us each on the device — is the one part of the path that does not shrink with N)."""
+    return max(host_threads(), 16 * world)
+
+
 def make_config(S, world, chunks):
     """One dict for both arms (the driver compares them)."""
     total = S * world
     return {"workload": f"{S} distinct-message signature sets per GPU = per-GPU share of BASELINE configs[4] "
                         f"(1M sets on 8 GPUs); one batch of {total} sets per step; sets = blsgpu_make_sets(seed {SEED})",
             "sets_per_step": total, "rlc_chunks": chunks,
-            "rlc_chunks_note": "tp.numThreads the drop-in passes = host hardware threads (same as the reference arm's threads)",
+            "rlc_chunks_note": "tp.numThreads the drop-in passes: max(host hardware threads, 16 per GPU); chunk_sweep has 0 / 16 / 64 / 1024",
             "l2": "GPU arm: 256 MiB flush write between steps",
             "partial_exchange": "NCCL all_gather of one 576-byte Fp12 per rank (one collective per step)" if world > 1 else "none"}
 
@@ -102,7 +109,7 @@ def run_reference(args):
     cores = br.ncores()
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     S = args.sets_per_gpu
-    chunks = args.chunks if args.chunks >= 0 else cores
+    chunks = args.chunks if args.chunks >= 0 else default_chunks(world)
     srb = hashlib.sha256(b"Mr F was here").digest()
     n = max(64, min(S * world, 1200 * cores))              # ~1-2 s of CPU work per step
     sets = br.make_sets_device_recipe(SEED, 0, n)          # first n sets of the timed workload, all distinct
@@ -313,7 +320,7 @@ def main():
     L = bg.lib()
     S = args.sets_per_gpu
     total = S * world
-    chunks = args.chunks if args.chunks >= 0 else host_threads()
+    chunks = args.chunks if args.chunks >= 0 else default_chunks(world)
     first = rank * S
     srb = hashlib.sha256(b"Mr F was here").digest()
 
@@ -332,7 +339,6 @@ def main():
     assert rc == 0, cache.last_error()
     h_sets = torch.empty(S * 320, dtype=torch.uint8).pin_memory()
     h_sets.copy_(d_sets)
-    d_stage = torch.empty(S * 320, dtype=torch.uint8, device=dev)      # e2e staging target (N > 1)
     d_partial = torch.zeros(576, dtype=torch.uint8, device=dev)
     d_all = torch.zeros(world * 576, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -394,9 +400,19 @@ def main():
         rc = L.blsgpu_batch_verify(h, c_pageable, S, srb, chunks, None, gt)
         assert rc == 1, cache.last_error()
 
+    h_part = torch.zeros(576, dtype=torch.uint8).pin_memory()
+    c_flag = C.c_int(0)
+
     def e2e_ranks():
-        d_stage.copy_(h_sets, non_blocking=True)          # H2D of this step's inputs from pinned memory
-        step(d_stage.data_ptr())                          # finalize_dev reads the verdict + GT back (D2H)
+        # the host-buffer share call of the ABI: H2D (overlapped with the hash inside the library), the share's pipeline,
+        # its 576-byte partial back on the host; then the exchange and the one final exponentiation
+        rc = L.blsgpu_partial(h, C.c_void_p(h_sets.data_ptr()), 0, S, first, total, srb, chunks, None,
+                              C.c_void_p(h_part.data_ptr()), C.byref(c_flag))
+        assert rc == 0, cache.last_error()
+        d_partial.copy_(h_part, non_blocking=True)
+        dist.all_gather_into_tensor(d_all, d_partial)
+        rc = L.blsgpu_finalize_dev(h, C.c_void_p(d_all.data_ptr()), world, None, gt)
+        assert rc == 1, cache.last_error()
 
     for _ in range(max(args.warmup, 3)):
         resident()
@@ -425,7 +441,8 @@ def main():
         for _ in range(2):
             e2e_ranks()
         ms_e2e = timed(e2e_ranks, args.steps)
-        e2e_extra = {"call": "per rank: pinned H2D copy + blsgpu_partial_dev + NCCL all_gather(576 B) + blsgpu_finalize_dev"}
+        e2e_extra = {"call": "per rank: blsgpu_partial(pinned host share) -> 576-byte partial on the host -> NCCL all_gather(576 B) "
+                             "-> blsgpu_finalize_dev"}
     value = total * args.steps / (ms_total * 1e-3)
     e2e_value = total * args.steps / (ms_e2e * 1e-3)
 

@@ -215,8 +215,13 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
         ctx->ev_valid[i] = true;
     }
-    if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
+    // the side streams carry the scalar chain (a block that needs a whole SM to itself) and the signature-side sum:
+    // highest priority, so that when they become runnable together with a grid that fills the machine (the hash kernel
+    // behind a caller's H2D copy on the main stream) their blocks are placed first
+    int pri_lo = 0, pri_hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&pri_lo, &pri_hi) != cudaSuccess) { cudaGetLastError(); pri_hi = 0; }
+    if ((e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, pri_hi)) != cudaSuccess) return bad("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithPriority(&ctx->side2, cudaStreamNonBlocking, pri_hi)) != cudaSuccess) return bad("cudaStreamCreate", e);
     if (getenv("BLSGPU_SIDE_STREAM")) ctx->use_side = atoi(getenv("BLSGPU_SIDE_STREAM")) != 0;
     if (getenv("BLSGPU_GRAPH")) ctx->use_graph = atoi(getenv("BLSGPU_GRAPH")) != 0;
     if ((e = cudaEventCreateWithFlags(&ctx->ev_share, cudaEventDisableTiming)) != cudaSuccess) return bad("cudaEventCreate", e);
@@ -711,7 +716,9 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     if (sliced) {
         // hashed piece by piece above
     } else if (small_hash) {
-        k_hash_map_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, sm_hash_in);
+        static const int map2 = getenv("BLSGPU_MAP_LANES2") ? atoi(getenv("BLSGPU_MAP_LANES2")) : 1;
+        if (map2) k_hash_map_lanes2<<<nblk(2 * n, 64), 64, 0, s>>>(d_sets, nullptr, nullptr, nullptr, 0, n, sm_hash_in);
+        else k_hash_map_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, sm_hash_in);
         launch_prog_many(ctx, p_cof, s, n, sm_hash_in, 6, nullptr, 0, sm_hash_out, 6);
         k_g2_hom_to_jac<<<nblk(n), 128, 0, s>>>(sm_hash_out, n, ctx->d_H);
         ctx->launches += 2;
@@ -1023,10 +1030,12 @@ extern "C" int blsgpu_partial(blsgpu_ctx *ctx, const void *sets, int sets_on_dev
     const sigset *d = (const sigset *)sets;
     if (sets_on_device && ((uintptr_t)sets & 15)) return fail(ctx, BLSGPU_ERR_ARG, "device sets pointer must be 16-byte aligned (TMA staging)");
     if (!sets_on_device) {
-        CK(cudaMemcpyAsync(ctx->d_sets, sets, n * sizeof(sigset), cudaMemcpyHostToDevice, s));
+        if (!sets) return fail(ctx, BLSGPU_ERR_ARG, "sets is NULL");
+        ctx->h_src = (const uint8_t *)sets;                  // run_partial_impl issues the copy (whole, or in overlapped pieces)
         d = ctx->d_sets;
     }
     int rc = run_partial(ctx, d, n, first, total_n, srb, chunks, scalars, 0);
+    ctx->h_src = nullptr;
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_partials, 576, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_pinned + 576, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1126,7 +1135,7 @@ extern "C" int blsgpu_test_small_hash(blsgpu_ctx *ctx, const void *sets320, size
     if (rc) return rc;
     fp *hin = ctx->d_small, *hout = hin + 6 * SMALL_ROUTE_MAX;
     CK(cudaMemcpyAsync(ctx->d_sets, sets320, n * 320, cudaMemcpyHostToDevice, s));
-    k_hash_map_pair<<<nblk(2 * n), 128, 0, s>>>(ctx->d_sets, n, hin);
+    k_hash_map_lanes2<<<nblk(2 * n, 64), 64, 0, s>>>(ctx->d_sets, nullptr, nullptr, nullptr, 0, n, hin);
     launch_prog_many(ctx, p_cof, s, n, hin, 6, nullptr, 0, hout, 6);
     CK(cudaGetLastError());
     if (out_in) CK(cudaMemcpyAsync(out_in, hin, n * 6 * sizeof(fp), cudaMemcpyDeviceToHost, s));
@@ -1238,7 +1247,9 @@ static int verify_pairs_dev(blsgpu_ctx *ctx, const g1_aff *d_pks, size_t n, cons
         if (rcp) return rcp;
         if (!ctx->d_small) CK(cudaMalloc((void **)&ctx->d_small, (size_t)SMALL_ROUTE_MAX * SMALL_FP_PER_SET * sizeof(fp)));
         fp *hin = ctx->d_small, *hout = hin + 6 * SMALL_ROUTE_MAX;
-        k_hash_map_pair_msgs<<<nblk(2 * n), 128, 0, s>>>(d_msgs, d_offs, d_dst, (uint32_t)dst_len, n, hin);
+        static const int map2 = getenv("BLSGPU_MAP_LANES2") ? atoi(getenv("BLSGPU_MAP_LANES2")) : 1;
+        if (map2) k_hash_map_lanes2<<<nblk(2 * n, 64), 64, 0, s>>>(nullptr, d_msgs, d_offs, d_dst, (uint32_t)dst_len, n, hin);
+        else k_hash_map_pair_msgs<<<nblk(2 * n), 128, 0, s>>>(d_msgs, d_offs, d_dst, (uint32_t)dst_len, n, hin);
         launch_prog_many(ctx, p_cof, s, n, hin, 6, nullptr, 0, hout, 6);
         k_g2_hom_to_affine<<<(unsigned)n, 32, 0, s>>>(hout, n, ctx->d_Q);
         ctx->launches += 2;

@@ -155,6 +155,15 @@ BLS_FN void hash_to_g2_jac(g2_jac &out, const uint8_t *msg, size_t msg_len, cons
     map_to_g2(out, u0, u1);
 }
 
+#ifdef __CUDACC__
+// H(msg) for the 32-byte message of a SignatureSet under DST_ETH2 (bls_sig_min_pubkey.nim:31)
+BLS_FN void hash_to_g2_jac_eth2(g2_jac &out, const uint8_t *msg32) {
+    fp2 u0, u1;
+    hash_to_field_fp2x2_eth2(u0, u1, msg32);
+    map_to_g2(out, u0, u1);
+}
+#endif
+
 // Zcash compressed encoding of an affine G2 point (e2.c:231-253): x.im || x.re big-endian, flags in byte 0
 BLS_FN void g2_compress(uint8_t *out, const g2_aff &p) {
     if (aff_is_inf(p)) {

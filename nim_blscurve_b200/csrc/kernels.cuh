@@ -32,10 +32,7 @@ struct sigset { g1_aff pk; uint8_t msg[32]; g2_aff sig; };
 static_assert(sizeof(sigset) == 320, "SignatureSet layout (bls_batch_verifier.nim:34)");
 static_assert(sizeof(fp12) == 576 && sizeof(g2_jac) == 288 && sizeof(g1_jac) == 144, "layout");
 
-// blscurve/bls_sig_min_pubkey.nim:31
-__device__ __constant__ const uint8_t DST_ETH2[43] = {
-    'B','L','S','_','S','I','G','_','B','L','S','1','2','3','8','1','G','2','_','X','M','D',':','S','H','A','-',
-    '2','5','6','_','S','S','W','U','_','R','O','_','P','O','P','_'};
+// DST_ETH2 (blscurve/bls_sig_min_pubkey.nim:31): sha256.cuh
 
 struct words8 { uint32_t w[8]; };   // a 32-byte string as big-endian words
 
@@ -140,16 +137,14 @@ __global__ void BLS_LB k_hash_sets(const sigset *sets, size_t n, g2_jac *H) {
     size_t i = base + threadIdx.x;
     if (i >= n) return;
     alignas(16) uint8_t msg[32];
-    uint8_t dst[43];
     {
         const uint4 *m = (const uint4 *)(tile + 32 * threadIdx.x);
         uint4 m0 = m[0], m1 = m[1];
         *(uint4 *)msg = m0;
         *(uint4 *)(msg + 16) = m1;
     }
-    for (int k = 0; k < 43; k++) dst[k] = DST_ETH2[k];
     g2_jac h;
-    hash_to_g2_jac(h, msg, 32, dst, 43);
+    hash_to_g2_jac_eth2(h, msg);
     H[i] = h;
 }
 
@@ -192,15 +187,13 @@ __global__ void BLS_LB k_hash_sets_lanes2(const sigset *sets, size_t n, g2_jac *
     const size_t i = base + (threadIdx.x >> 1);
     if (i >= n) return;                                    // both lanes of a pair leave together
     alignas(16) uint8_t msg[32];
-    uint8_t dst[43];
     {
         const uint4 *m = (const uint4 *)(tile + 32 * (threadIdx.x >> 1));
         *(uint4 *)msg = m[0];
         *(uint4 *)(msg + 16) = m[1];
     }
-    for (int k = 0; k < 43; k++) dst[k] = DST_ETH2[k];
     g2h_jac h;
-    hash_to_g2_pair(h, msg, 32, dst, 43);
+    hash_to_g2_pair(h, msg, 32, nullptr, 0);
     fp *out = (fp *)&H[i] + (h_odd() ? 1 : 0);             // g2_jac = x.c0 x.c1 y.c0 y.c1 z.c0 z.c1
     out[0] = h.x.v;
     out[2] = h.y.v;
@@ -259,6 +252,29 @@ __global__ void BLS_LB k_hash_map_pair(const sigset *sets, size_t n, fp *hom) {
     pt_add(q, q, other, &SSWU_A);
     iso3_g2(q, q);
     g2_jac_to_hom(hom + 6 * i, q);
+}
+// The same on lane pairs with every Fp2 operation split over the two lanes (pair_route.cuh): the two square-root chains
+// still run one map per lane, and the Fp2 stretches around them (SSWU, sum on E2', isogeny) take half as long.
+// msgs == nullptr: the messages are those of the signature sets (32 bytes, DST of bls_sig_min_pubkey.nim:31).
+__global__ void BLS_LB k_hash_map_lanes2(const sigset *sets, const uint8_t *msgs, const uint32_t *offs, const uint8_t *dst_g,
+                                         uint32_t dst_len, size_t n, fp *hom) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = t >> 1;
+    if (i >= n) return;
+    g2h_jac q;
+    if (msgs) {
+        hash_map_to_e2_pair(q, msgs + offs[i], offs[i + 1] - offs[i], dst_g, dst_len);
+    } else {
+        uint8_t msg[32];
+        for (int k = 0; k < 32; k++) msg[k] = sets[i].msg[k];
+        hash_map_to_e2_pair(q, msg, 32, nullptr, 0);
+    }
+    fp2h X, Y, Z;
+    jac_to_hom_pair(X, Y, Z, q);
+    fp *out = hom + 6 * i + (h_odd() ? 1 : 0);
+    out[0] = X.v;
+    out[2] = Y.v;
+    out[4] = Z.v;
 }
 // the same for the verify entry points: arbitrary messages (msgs + offs[i] .. offs[i+1]) and domain separation tag
 __global__ void BLS_LB k_hash_map_pair_msgs(const uint8_t *msgs, const uint32_t *offs, const uint8_t *dst, uint32_t dst_len,

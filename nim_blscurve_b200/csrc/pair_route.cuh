@@ -159,14 +159,16 @@ BLS_NOINLINE void clear_cofactor_pair(g2h_jac &out, const g2h_jac &p) {
     pt_add(out, t3, n);
 }
 
-// H(msg) as halves of a Jacobian point.  Both lanes of the pair hash the message (the XMD is 18 SHA-256 blocks, ~1 % of
-// the work) and each keeps its halves of u0, u1.
-BLS_NOINLINE void hash_to_g2_pair(g2h_jac &out, const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len) {
+// Everything of H(msg) up to the cofactor clearing — XMD, the two SSWU maps, their sum on E2', the 3-isogeny — as halves
+// of a Jacobian point on E2.  Both lanes of the pair hash the message (the XMD is 18 SHA-256 blocks, ~1 % of the work)
+// and each keeps its halves of u0, u1.
+BLS_NOINLINE void hash_map_to_e2_pair(g2h_jac &out, const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len) {
     const bool odd = h_odd();
     fp2h u0, u1;
     {
         uint32_t xmd[64];
-        expand_message_xmd_256(xmd, msg, msg_len, dst, dst_len);
+        if (dst) expand_message_xmd_256(xmd, msg, msg_len, dst, dst_len);
+        else expand_message_xmd_256_eth2(xmd, msg);      // dst == nullptr: 32-byte message under DST_ETH2
         fp_from_be64(u0.v, xmd + (odd ? 16 : 0));
         fp_from_be64(u1.v, xmd + (odd ? 48 : 32));
     }
@@ -197,8 +199,27 @@ BLS_NOINLINE void hash_to_g2_pair(g2h_jac &out, const uint8_t *msg, size_t msg_l
     fp2h a;
     hk(a, SSWU_A);
     pt_add(q0, q0, q1, &a);
-    iso3_pair(q0, q0);
-    clear_cofactor_pair(out, q0);
+    iso3_pair(out, q0);
+}
+// H(msg) as halves of a Jacobian point
+BLS_NOINLINE void hash_to_g2_pair(g2h_jac &out, const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len) {
+    g2h_jac q;
+    hash_map_to_e2_pair(q, msg, msg_len, dst, dst_len);
+    clear_cofactor_pair(out, q);
+}
+// this lane's halves of the homogeneous form (X Z : Y : Z^3) of a Jacobian point; infinity -> (0 : 1 : 0)
+__device__ __forceinline__ void jac_to_hom_pair(fp2h &X, fp2h &Y, fp2h &Z, const g2h_jac &p) {
+    if (pt_is_inf(p)) {
+        f_set_zero(X);
+        f_set_one(Y);
+        f_set_zero(Z);
+    } else {
+        fp2h z2;
+        h_mul(X, p.x, p.z);
+        Y = p.y;
+        h_sqr(z2, p.z);
+        h_mul(Z, z2, p.z);
+    }
 }
 
 // ---- Miller-loop lines on a pair (line_dbl_proj / line_add_proj / miller_lines of pairing.cuh) -----------------------

@@ -151,6 +151,60 @@ BLS_FN void expand_message_xmd_256(uint32_t *out, const uint8_t *msg, size_t msg
     }
 }
 
+// blscurve/bls_sig_min_pubkey.nim:31
+BLS_TABLE uint8_t DST_ETH2[43] = {
+    'B','L','S','_','S','I','G','_','B','L','S','1','2','3','8','1','G','2','_','X','M','D',':','S','H','A','-',
+    '2','5','6','_','S','S','W','U','_','R','O','_','P','O','P','_'};
+
+#ifdef __CUDACC__
+// expand_message_xmd(msg, DST_ETH2, 256) for the 32-byte messages of a SignatureSet: the 18 blocks are assembled as
+// words (no byte-wise absorption) and compressed in registers.  Same 64 output words as expand_message_xmd_256.
+//   b0 = H(Z_pad | msg | 01 00 | 00 | DST | 2b): after the pre-absorbed Z_pad block, 79 bytes = blocks
+//        [msg(32) 01 00 00 DST[0..28]] [DST[29..42] 2b 80 0.. len=1144]
+//   bi = H(x(32) | i | DST | 2b), 77 bytes = [x(32) i DST[0..30]] [DST[31..42] 2b 80 0.. len=616]
+__device__ __forceinline__ uint32_t dst_eth2_byte(int k) { return k < 43 ? (uint32_t)DST_ETH2[k] : (k == 43 ? 0x2bu : (k == 44 ? 0x80u : 0u)); }
+// big-endian word of the virtual string DST | 2b | 80 | 00.. starting at byte offset k
+__device__ __forceinline__ uint32_t dst_eth2_word(int k) {
+    return (dst_eth2_byte(k) << 24) | (dst_eth2_byte(k + 1) << 16) | (dst_eth2_byte(k + 2) << 8) | dst_eth2_byte(k + 3);
+}
+BLS_NOINLINE void expand_message_xmd_256_eth2(uint32_t *out, const uint8_t *msg32) {
+    uint32_t h[8], w[16], b0[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = SHA256_ZPAD_STATE[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        w[i] = ((uint32_t)msg32[4 * i] << 24) | ((uint32_t)msg32[4 * i + 1] << 16) | ((uint32_t)msg32[4 * i + 2] << 8) | msg32[4 * i + 3];
+    w[8] = 0x01000000u | dst_eth2_byte(0);                       // 01 00 00 DST[0]
+#pragma unroll
+    for (int i = 9; i < 16; i++) w[i] = dst_eth2_word(1 + 4 * (i - 9));       // DST[1..28]
+    sha256_block_regs(h, w);
+#pragma unroll
+    for (int i = 0; i < 14; i++) w[i] = dst_eth2_word(29 + 4 * i);            // DST[29..42] 2b 80 00..
+    w[14] = 0;
+    w[15] = 1144;
+    sha256_block_regs(h, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) b0[i] = h[i];
+    for (int blk = 1; blk <= 8; blk++) {
+        h[0] = 0x6a09e667u; h[1] = 0xbb67ae85u; h[2] = 0x3c6ef372u; h[3] = 0xa54ff53au;
+        h[4] = 0x510e527fu; h[5] = 0x9b05688cu; h[6] = 0x1f83d9abu; h[7] = 0x5be0cd19u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = blk == 1 ? b0[i] : (b0[i] ^ out[8 * (blk - 2) + i]);
+        w[8] = ((uint32_t)blk << 24) | (dst_eth2_byte(0) << 16) | (dst_eth2_byte(1) << 8) | dst_eth2_byte(2);
+#pragma unroll
+        for (int i = 9; i < 16; i++) w[i] = dst_eth2_word(3 + 4 * (i - 9));   // DST[3..30]
+        sha256_block_regs(h, w);
+#pragma unroll
+        for (int i = 0; i < 14; i++) w[i] = dst_eth2_word(31 + 4 * i);        // DST[31..42] 2b 80 00..
+        w[14] = 0;
+        w[15] = 616;
+        sha256_block_regs(h, w);
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[8 * (blk - 1) + i] = h[i];
+    }
+}
+#endif
+
 // 64 bytes big-endian (16 BE words, most significant first) -> Fp in Montgomery form
 BLS_FN void fp_from_be64(fp &r, const uint32_t *be) {
     fp lo, hi, t0, t1;
@@ -171,5 +225,17 @@ BLS_FN void hash_to_field_fp2x2(fp2 &u0, fp2 &u1, const uint8_t *msg, size_t msg
     fp_from_be64(u1.c0, xmd + 32);
     fp_from_be64(u1.c1, xmd + 48);
 }
+
+#ifdef __CUDACC__
+// the same for the 32-byte message of a SignatureSet under DST_ETH2 (word-level XMD, blocks compressed in registers)
+BLS_FN void hash_to_field_fp2x2_eth2(fp2 &u0, fp2 &u1, const uint8_t *msg32) {
+    uint32_t xmd[64];
+    expand_message_xmd_256_eth2(xmd, msg32);
+    fp_from_be64(u0.c0, xmd);
+    fp_from_be64(u0.c1, xmd + 16);
+    fp_from_be64(u1.c0, xmd + 32);
+    fp_from_be64(u1.c1, xmd + 48);
+}
+#endif
 
 }  // namespace bls
