@@ -60,7 +60,7 @@ struct blsgpu_ctx {
     int launches = 0;
     msm_state msm;
     // warp-cooperative tail programs (fpprog.hpp), compiled on first use and kept on the device
-    struct dev_prog { uint32_t *d = nullptr; int nslots = 0, nrounds = 0; };
+    struct dev_prog { uint32_t *d = nullptr; int nslots = 0, nrounds = 0, version = 1; };
     std::map<int, dev_prog> combine_progs, final_progs, norm_progs, set_progs, prod_progs;   // keyed by segment count / partial count
     fp *d_small_lines = nullptr;                             // 68 x 6 field elements per pair (small-batch route)
     fp *d_small = nullptr;                                   // per-set program inputs/outputs of the small-batch route
@@ -360,6 +360,7 @@ static int get_prog(blsgpu_ctx *ctx, int kind, int key, blsgpu_ctx::dev_prog &ou
     blsgpu_ctx::dev_prog dp;
     dp.nslots = P.nslots;
     dp.nrounds = P.nrounds;
+    dp.version = P.version;
     CK(cudaMalloc((void **)&dp.d, P.words.size() * 4));
     // stream-ordered upload, completed before the host vector goes away (first use only)
     CK(cudaMemcpyAsync(dp.d, P.words.data(), P.words.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -373,9 +374,14 @@ static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp 
     size_t smem = (size_t)p.nslots * sizeof(fp);
     if (smem > 48 * 1024) {
         // per context, not per process: the attribute belongs to the function on ONE device
-        if (!ctx->prog_smem_raised) { CK(cudaFuncSetAttribute(k_fp_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); ctx->prog_smem_raised = true; }
+        if (!ctx->prog_smem_raised) {
+            CK(cudaFuncSetAttribute(k_fp_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CK(cudaFuncSetAttribute(k_fp_program2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            ctx->prog_smem_raised = true;
+        }
     }
-    k_fp_program<<<1, 32, smem, ctx->stream>>>(p.d, in0, in1, ctx->d_consts, out0, 0, 0, 0);
+    if (p.version == 2) k_fp_program2<<<1, 32, smem, ctx->stream>>>(p.d, in0, in1, ctx->d_consts, out0, 0, 0, 0);
+    else k_fp_program<<<1, 32, smem, ctx->stream>>>(p.d, in0, in1, ctx->d_consts, out0, 0, 0, 0);
     ctx->launches++;
     return 0;
 }
@@ -383,10 +389,14 @@ static int launch_prog(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, const fp 
 // one warp per instance: n instances of a per-set program on stream st, strides in field elements
 static int launch_prog_many(blsgpu_ctx *ctx, const blsgpu_ctx::dev_prog &p, cudaStream_t st, size_t n, const fp *in0, size_t s_in0,
                             const fp *in1, size_t s_in1, fp *out0, size_t s_out, bool stream_outputs = false) {
-    if (stream_outputs)
-        k_fp_program_stream<<<(unsigned)n, 32, (size_t)p.nslots * sizeof(fp), st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
+    const size_t smem = (size_t)p.nslots * sizeof(fp);
+    if (p.version == 2) {
+        if (stream_outputs) k_fp_program2_stream<<<(unsigned)n, 32, smem, st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
+        else k_fp_program2<<<(unsigned)n, 32, smem, st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
+    } else if (stream_outputs)
+        k_fp_program_stream<<<(unsigned)n, 32, smem, st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
     else
-        k_fp_program<<<(unsigned)n, 32, (size_t)p.nslots * sizeof(fp), st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
+        k_fp_program<<<(unsigned)n, 32, smem, st>>>(p.d, in0, in1, ctx->d_consts, out0, s_in0, s_in1, s_out);
     ctx->launches++;
     return 0;
 }
@@ -532,8 +542,12 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot, size_t pair0 = 0) {
             rc = get_prog(ctx, 4, 8, p8);
             if (rc) return rc;
             if (cols & 7) { k_fp12_pad_one<<<nseg, 32, 0, s>>>(cur, stride, cols); ctx->launches++; }
-            k_fp_program_rows<<<(unsigned)((size_t)nseg * m), 32, (size_t)p8.nslots * sizeof(fp), s>>>(
-                p8.d, (const fp *)cur, ctx->d_consts, (fp *)other, (unsigned)m, stride, m_stride);
+            if (p8.version == 2)
+                k_fp_program2_rows<<<(unsigned)((size_t)nseg * m), 32, (size_t)p8.nslots * sizeof(fp), s>>>(
+                    p8.d, (const fp *)cur, ctx->d_consts, (fp *)other, (unsigned)m, stride, m_stride);
+            else
+                k_fp_program_rows<<<(unsigned)((size_t)nseg * m), 32, (size_t)p8.nslots * sizeof(fp), s>>>(
+                    p8.d, (const fp *)cur, ctx->d_consts, (fp *)other, (unsigned)m, stride, m_stride);
             ctx->launches++;
             fp12 *t = cur; cur = other; other = t;
             cols = m;
@@ -541,8 +555,12 @@ static int run_miller(blsgpu_ctx *ctx, size_t np, int slot, size_t pair0 = 0) {
         }
         rc = get_prog(ctx, 4, (int)cols, pm);
         if (rc) return rc;
-        k_fp_program_rows<<<(unsigned)nseg, 32, (size_t)pm.nslots * sizeof(fp), s>>>(pm.d, (const fp *)cur, ctx->d_consts,
-                                                                                    (fp *)ctx->d_seg, 1u, stride, 1);
+        if (pm.version == 2)
+            k_fp_program2_rows<<<(unsigned)nseg, 32, (size_t)pm.nslots * sizeof(fp), s>>>(pm.d, (const fp *)cur, ctx->d_consts,
+                                                                                         (fp *)ctx->d_seg, 1u, stride, 1);
+        else
+            k_fp_program_rows<<<(unsigned)nseg, 32, (size_t)pm.nslots * sizeof(fp), s>>>(pm.d, (const fp *)cur, ctx->d_consts,
+                                                                                        (fp *)ctx->d_seg, 1u, stride, 1);
         ctx->launches++;
     } else if (ncols > BLS_ACC_BS) {
         dim3 grid((unsigned)ncols2, nseg);

@@ -13,6 +13,7 @@
 // execute them on the CPU against the straight-line formulas of tower.cuh / pairing.cuh.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <queue>
 #include <utility>
@@ -252,8 +253,26 @@ inline void store12(V12 a, int buf, int base) {
 struct Program {
     std::vector<uint32_t> words;      // [nrounds, nslots, n_in, n_out] + in table + out table + rounds
     int nrounds = 0, nmul_rounds = 0, nslots = 0, nops = 0;
+    int version = 1;                  // 1: 32 words per round (mul / add / sub); 2: 32 x 4 words per round (mul / lincomb)
     bool ok = false;
 };
+
+// Format 2 ("lincomb" programs; executed by k_fp_program2 / hostsim run_program2).  A round is 32 x 4 words, lane l owns
+// words [4 l, 4 l + 4):
+//   w0 = op:2 | dst:10 | npos:3 | nneg:3 | term6:14        op 1 = MUL, 2 = LIN, 0 = idle (w0 == 0) or STORE (w0 != 0)
+//   MUL   w1 = a:10 | b:10                                   slot[dst] = slot[a] * slot[b]
+//   LIN   terms t0..t6 (14 bits each: slot:10 | magnitude:4) in w1 = t0 | t1 << 14, w2 = t2 | t3 << 14, w3 = t4 | t5 << 14,
+//         t6 in w0; the first npos positions (from t0 up) are the positive terms, the last nneg positions (from t6 down)
+//         the negative ones:    slot[dst] = sum_pos mag * slot - sum_neg mag * slot   (mod p; fplin.cuh)
+//   STORE w1 = source slot, w2 = OUT0 index                 (streamed outputs)
+enum { LIN_MAXT = 7, LIN_MAXMAG = 15 };
+// programs are compiled to format 2 unless BLSGPU_PROG_FORMAT=1 (A/B runs) or a test overrides it
+static thread_local int g_format_override = 0;
+inline int program_format() {
+    if (g_format_override) return g_format_override;
+    static const int f = getenv("BLSGPU_PROG_FORMAT") ? atoi(getenv("BLSGPU_PROG_FORMAT")) : 2;
+    return f == 1 ? 1 : 2;
+}
 
 inline uint32_t enc(int op, int d, int a, int b) { return ((uint32_t)op << 30) | ((uint32_t)d << 20) | ((uint32_t)a << 10) | (uint32_t)b; }
 
@@ -374,6 +393,204 @@ inline Program compile(const Builder &B, int slack = 40) {
     return P;
 }
 
+// ---- format 2: every linear expression flattened into one combination ---------------------------------------------
+// Linear nodes (add / sub) are not operations of their own any more: each is expressed as a combination
+// sum coef * base over MATERIALISED nodes (leaves, products, and those linear nodes that had to be given a slot: operands
+// of a product, program outputs, and cut points where a combination would exceed 7 terms or a magnitude of 15).  Between
+// two levels of products there is then ONE round of combinations instead of three to six rounds of two-operand additions.
+inline Program compile2(const Builder &B, int slack = 40) {
+    const int N = (int)B.nodes.size();
+    Program P;
+    P.version = 2;
+    typedef std::vector<std::pair<int, int>> Form;            // (materialised node, coefficient), sorted by node
+    std::vector<Form> form(N);
+    std::vector<char> mat(N, 0), is_lin(N, 0);
+    auto combine = [&](const Form &fa, const Form &fb, int sb) {
+        Form r;
+        size_t i = 0, j = 0;
+        while (i < fa.size() || j < fb.size()) {
+            if (j >= fb.size() || (i < fa.size() && fa[i].first < fb[j].first)) r.push_back(fa[i++]);
+            else if (i >= fa.size() || fb[j].first < fa[i].first) { r.push_back({fb[j].first, sb * fb[j].second}); j++; }
+            else { int c = fa[i].second + sb * fb[j].second; if (c) r.push_back({fa[i].first, c}); i++; j++; }
+        }
+        return r;
+    };
+    auto fits = [&](const Form &f) {
+        if ((int)f.size() > LIN_MAXT) return false;
+        for (const auto &t : f) if (t.second > LIN_MAXMAG || t.second < -LIN_MAXMAG) return false;
+        return true;
+    };
+    auto ref = [&](int x) -> Form {                            // how a consumer sees node x
+        if (x == 0) return Form();
+        if (!is_lin[x] || mat[x]) return Form{{x, 1}};
+        return form[x];
+    };
+    for (int n = 1; n < N; n++) {
+        const Node &nd = B.nodes[n];
+        if (nd.op == OP_LEAF) { mat[n] = 1; continue; }
+        if (nd.op == OP_MUL) {
+            mat[n] = 1;
+            if (is_lin[nd.a]) mat[nd.a] = 1;                   // operands of a product need a slot
+            if (is_lin[nd.b]) mat[nd.b] = 1;
+            continue;
+        }
+        is_lin[n] = 1;
+        const int sb = nd.op == OP_SUB ? -1 : 1;
+        Form f = combine(ref(nd.a), ref(nd.b), sb);
+        if (!fits(f)) {                                        // cut: give the larger operand a slot of its own, then the other
+            const bool ca = is_lin[nd.a] && !mat[nd.a], cb = is_lin[nd.b] && !mat[nd.b];
+            const size_t sa = ca ? form[nd.a].size() : 0, sbz = cb ? form[nd.b].size() : 0;
+            if (ca && (!cb || sa >= sbz)) mat[nd.a] = 1; else if (cb) mat[nd.b] = 1;
+            f = combine(ref(nd.a), ref(nd.b), sb);
+            if (!fits(f)) {
+                if (is_lin[nd.a]) mat[nd.a] = 1;
+                if (is_lin[nd.b]) mat[nd.b] = 1;
+                f = combine(ref(nd.a), ref(nd.b), sb);
+            }
+        }
+        form[n] = f;
+    }
+    for (const IoRef &o : B.outputs) if (is_lin[o.node]) mat[o.node] = 1;
+    // operations = products and materialised combinations that an output needs
+    std::vector<char> need(N, 0);
+    for (const IoRef &o : B.outputs) need[o.node] = 1;
+    for (int n = N - 1; n >= 1; n--) {
+        if (!need[n]) continue;
+        const Node &nd = B.nodes[n];
+        if (nd.op == OP_MUL) { need[nd.a] = 1; need[nd.b] = 1; }
+        else if (is_lin[n]) for (const auto &t : form[n]) need[t.first] = 1;
+    }
+    need[0] = 0;
+    auto is_op = [&](int n) { return need[n] && (B.nodes[n].op == OP_MUL || (is_lin[n] && mat[n])); };
+    auto deps = [&](int n, std::vector<int> &out) {
+        out.clear();
+        if (B.nodes[n].op == OP_MUL) { out.push_back(B.nodes[n].a); if (B.nodes[n].b != B.nodes[n].a) out.push_back(B.nodes[n].b); }
+        else for (const auto &t : form[n]) out.push_back(t.first);
+    };
+    // priority: longest weighted path to an output (a product costs about twice a combination)
+    std::vector<int> height(N, 0);
+    std::vector<int> dl;
+    for (int n = N - 1; n >= 1; n--) {
+        if (!is_op(n)) continue;
+        const int h = height[n] + (B.nodes[n].op == OP_MUL ? 10 : 5);
+        deps(n, dl);
+        for (int d : dl) height[d] = std::max(height[d], h);
+    }
+    std::vector<std::vector<int>> users(N);
+    std::vector<int> pending(N, 0), round_of(N, -1);
+    typedef std::pair<int, int> PQE;
+    std::priority_queue<PQE> q_mul, q_lin;
+    auto push_ready = [&](int n) { (B.nodes[n].op == OP_MUL ? q_mul : q_lin).push({height[n], -n}); };
+    for (int n = 1; n < N; n++) {
+        if (!is_op(n)) continue;
+        deps(n, dl);
+        int cnt = 0;
+        for (int d : dl) if (d != 0 && B.nodes[d].op != OP_LEAF) { users[d].push_back(n); cnt++; }
+        pending[n] = cnt;
+        if (cnt == 0) push_ready(n);
+    }
+    std::vector<std::vector<int>> rounds;
+    std::vector<char> round_is_mul;
+    while (!q_mul.empty() || !q_lin.empty()) {
+        const int hmax = std::max(q_mul.empty() ? -1 : q_mul.top().first, q_lin.empty() ? -1 : q_lin.top().first);
+        // a ready combination that is less urgent than every ready product joins a later round of combinations
+        const bool is_mul = q_lin.empty() || q_lin.top().first < hmax - slack ||
+                            (!q_mul.empty() && q_lin.top().first + LIN_DEFER <= q_mul.top().first);
+        std::priority_queue<PQE> &q = is_mul ? q_mul : q_lin;
+        std::vector<int> ops;
+        while (!q.empty() && (int)ops.size() < LANES && q.top().first >= hmax - slack) { ops.push_back(-q.top().second); q.pop(); }
+        const int r = (int)rounds.size();
+        for (int n : ops) round_of[n] = r;
+        for (int n : ops)
+            for (int u : users[n]) if (--pending[u] == 0) push_ready(u);
+        rounds.push_back(ops);
+        round_is_mul.push_back(is_mul);
+    }
+    // streamed outputs
+    std::vector<std::vector<std::pair<int, int>>> stores(rounds.size());
+    for (const IoRef &o : B.outputs) {
+        if (!o.stream) continue;
+        size_t q = (size_t)round_of[o.node] + 1;
+        while (q < rounds.size() && rounds[q].size() + stores[q].size() >= (size_t)LANES) q++;
+        if (q >= rounds.size()) { rounds.push_back({}); round_is_mul.push_back(0); stores.push_back({}); q = rounds.size() - 1; }
+        stores[q].push_back({o.node, o.idx});
+    }
+    // liveness and slots
+    const int NR = (int)rounds.size();
+    std::vector<int> last_use(N, -1);
+    for (int r = 0; r < NR; r++) {
+        for (int n : rounds[r]) { deps(n, dl); for (int d : dl) last_use[d] = r; }
+        for (const auto &st : stores[r]) last_use[st.first] = std::max(last_use[st.first], r);
+    }
+    for (const IoRef &o : B.outputs) if (!o.stream) last_use[o.node] = NR + 1;
+    last_use[0] = NR + 1;
+    std::vector<int> slot(N, -1);
+    slot[0] = 0;
+    std::priority_queue<int, std::vector<int>, std::greater<int>> free_slots;
+    int next_slot = 1;
+    auto alloc = [&]() { if (!free_slots.empty()) { int s = free_slots.top(); free_slots.pop(); return s; } return next_slot++; };
+    std::vector<std::vector<int>> expire(NR + 2);
+    std::vector<IoRef> ins;
+    for (const IoRef &in : B.inputs)
+        if (need[in.node]) {
+            ins.push_back(in);
+            slot[in.node] = alloc();
+            if (last_use[in.node] >= 0 && last_use[in.node] <= NR) expire[last_use[in.node]].push_back(in.node);
+        }
+    for (int r = 0; r < NR; r++) {
+        for (int n : rounds[r]) {
+            slot[n] = alloc();
+            if (last_use[n] <= NR) expire[last_use[n] < r ? r : last_use[n]].push_back(n);
+        }
+        for (int n : expire[r]) free_slots.push(slot[n]);
+    }
+    P.nslots = next_slot;
+    if (next_slot > MAX_SLOTS) return P;
+    std::vector<IoRef> outs;
+    for (const IoRef &o : B.outputs) if (!o.stream) outs.push_back(o);
+    for (const IoRef &o : outs) if (slot[o.node] < 0) return P;          // an output that is neither input nor operation
+    P.words = {(uint32_t)NR, (uint32_t)P.nslots, (uint32_t)ins.size(), (uint32_t)outs.size()};
+    for (const IoRef &in : ins) { P.words.push_back((uint32_t)slot[in.node]); P.words.push_back(((uint32_t)in.buf << 24) | (uint32_t)in.idx); }
+    for (const IoRef &o : outs) { P.words.push_back((uint32_t)slot[o.node]); P.words.push_back(((uint32_t)o.buf << 24) | (uint32_t)o.idx); }
+    while (P.words.size() % 4) P.words.push_back(0u);        // the rounds are read as 16-byte words
+    for (int r = 0; r < NR; r++) {
+        const int nops = (int)rounds[r].size();
+        for (int l = 0; l < LANES; l++) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (l < nops) {
+                const int n = rounds[r][l];
+                if (B.nodes[n].op == OP_MUL) {
+                    w[0] = (1u << 30) | ((uint32_t)slot[n] << 20);
+                    w[1] = (uint32_t)slot[B.nodes[n].a] | ((uint32_t)slot[B.nodes[n].b] << 10);
+                } else {
+                    uint32_t t[LIN_MAXT] = {0, 0, 0, 0, 0, 0, 0};
+                    int npos = 0, nneg = 0;
+                    for (const auto &tm : form[n]) {
+                        const uint32_t code = (uint32_t)slot[tm.first] | ((uint32_t)(tm.second < 0 ? -tm.second : tm.second) << 10);
+                        if (tm.second > 0) t[npos++] = code; else t[LIN_MAXT - 1 - nneg++] = code;
+                    }
+                    w[0] = (2u << 30) | ((uint32_t)slot[n] << 20) | ((uint32_t)npos << 17) | ((uint32_t)nneg << 14) | t[6];
+                    w[1] = t[0] | (t[1] << 14);
+                    w[2] = t[2] | (t[3] << 14);
+                    w[3] = t[4] | (t[5] << 14);
+                }
+                P.nops++;
+            } else if (l - nops < (int)stores[r].size()) {
+                const std::pair<int, int> &st = stores[r][l - nops];
+                w[0] = 1u;                                   // op 0, non-zero: STORE
+                w[1] = (uint32_t)slot[st.first];
+                w[2] = (uint32_t)st.second;
+            }
+            for (int k = 0; k < 4; k++) P.words.push_back(w[k]);
+        }
+        P.nmul_rounds += round_is_mul[r] ? 1 : 0;
+    }
+    P.nrounds = NR;
+    P.ok = true;
+    return P;
+}
+inline Program compile_any(const Builder &B, int slack = 40) { return program_format() == 2 ? compile2(B, slack) : compile(B, slack); }
+
 // ---- the three tail programs -------------------------------------------------------------------------
 // Horner over nseg Miller-loop segment products (IN0: nseg x 12 fp) -> rank partial (OUT0: 12 fp); mirrors
 // miller_combine() in pairing.cuh.  seg_len[j] = number of loop iterations of segment j.
@@ -387,7 +604,7 @@ inline Program build_combine(int nseg, const int *seg_len) {
     }
     store12(conj(acc), BUF_OUT0, 0);
     g_b = nullptr;
-    return compile(b);
+    return compile_any(b);
 }
 
 // product of `count` partials (IN0: count x 12 fp) followed by the final exponentiation -> OUT0: 12 fp.
@@ -409,7 +626,7 @@ inline Program build_final(int count, int inv_mode = INV_INLINE) {
     if (inv_mode != INV_EMIT_ARG) store12(r, BUF_OUT0, 0);
     g_inv_mode = INV_INLINE;
     g_b = nullptr;
-    return compile(b);
+    return compile_any(b);
 }
 
 // product of `count` Fp12 values (IN0: count x 12 fp) -> OUT0: 12 fp; balanced tree.  One warp per segment row of a small
@@ -428,7 +645,7 @@ inline Program build_fp12_product(int count) {
     }
     store12(v[0], BUF_OUT0, 0);
     g_b = nullptr;
-    return compile(b);
+    return compile_any(b);
 }
 
 // ---- G1 in homogeneous projective coordinates, complete formulas --------------------------------------------------
@@ -495,7 +712,7 @@ inline Program build_msm_horner_g1(int nwin, int c) {
     b.output(acc.y.id, BUF_OUT0, 1);
     b.output(acc.z.id, BUF_OUT0, 2);
     g_b = nullptr;
-    return compile(b);
+    return compile_any(b);
 }
 // the same over Fp2 for a G2 MSM (the signature sum of a batch): IN0 = nwin x 6 fp, OUT0[0..5]
 inline PT<V2> load_g2(int buf, int base);
@@ -512,7 +729,7 @@ inline Program build_msm_horner_g2(int nwin, int c) {
     store_g2(acc, BUF_OUT0, 0);
     g_b = nullptr;
     g_fp2_shallow = false;
-    return compile(b);
+    return compile_any(b);
 }
 
 // ---- per-set G2 programs of the small-batch route (one warp per signature set, k_fp_program_many) ----------------
@@ -555,7 +772,7 @@ inline Program build_g2_clear_cofactor() {
     store_g2(rcb_add(t3, rcb_neg(p)), BUF_OUT0, 0);
     g_b = nullptr;
     g_fp2_shallow = false;
-    return compile(b);
+    return compile_any(b);
 }
 // [k]Q for a 64-bit k given as 64 field elements 0 / 1 (IN1[0..63], least significant first; Montgomery form), Q
 // homogeneous in IN0[0..5]: double-and-always-add with the addend (b X : b Y + (1 - b) : b Z), which is Q for b = 1 and
@@ -577,7 +794,7 @@ inline Program build_g2_mul64() {
     store_g2(acc, BUF_OUT0, 0);
     g_b = nullptr;
     g_fp2_shallow = false;
-    return compile(b);
+    return compile_any(b);
 }
 
 // All 68 line triples of one Miller-loop pair (pairing.cuh miller_lines: 63 tangents + 5 chords in execution order, each
@@ -645,7 +862,7 @@ inline Program build_miller_lines() {
     g_fp2_shallow = false;
     // no deferral of off-critical-path operations: the line scalings are ready early, few, and their streamed results
     // free their slots at once — deferring them to the end is what would keep hundreds of values alive
-    return compile(b, 1 << 28);
+    return compile_any(b, 1 << 28);
 }
 
 }  // namespace fpprog

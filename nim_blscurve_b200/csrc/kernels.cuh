@@ -19,6 +19,7 @@
 #include "io.cuh"
 #include "pair_route.cuh"
 #include "tma_stage.cuh"
+#include "fplin.cuh"
 
 namespace bls {
 
@@ -736,6 +737,95 @@ __global__ void __launch_bounds__(32) k_fp_program(const uint32_t *prog, const f
 __global__ void __launch_bounds__(32) k_fp_program_stream(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst,
                                                           fp *out0, size_t s_in0, size_t s_in1, size_t s_out) {
     fp_program_body<true>(prog, in0, in1, cst, out0, s_in0, s_in1, s_out);
+}
+
+// ---- format 2 (fpprog.hpp compile2): rounds of products and rounds of linear combinations --------------------------
+// A round is 32 x 16 bytes; a LIN lane evaluates sum_pos mag * slot - sum_neg mag * slot (mod p) over up to seven
+// operands in one step (fplin.cuh), so the three to six addition levels that the tower formulas put between two
+// levels of products are ONE round.  Lanes of a round all hold the same kind of operation (or a STORE / nothing).
+template <bool STREAM>
+__device__ __forceinline__ void fp_program2_body(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst, fp *out0,
+                                                 size_t s_in0, size_t s_in1, size_t s_out) {
+    extern __shared__ uint4 sm4[];
+    fp *slots = (fp *)sm4;
+    const int lane = threadIdx.x;
+    if (s_in0 != ~(size_t)0) {
+        in0 += (size_t)blockIdx.x * s_in0;
+        if (in1) in1 += (size_t)blockIdx.x * s_in1;
+        out0 += (size_t)blockIdx.x * s_out;
+    }
+    const uint32_t nr = prog[0], nin = prog[2], nout = prog[3];
+    if (lane == 0) fp_set_zero(slots[0]);
+    for (uint32_t e = lane; e < nin; e += 32) {
+        uint32_t sl = prog[4 + 2 * e], ref = prog[5 + 2 * e], buf = ref >> 24, idx = ref & 0xffffffu;
+        const fp *src = buf == 0 ? in0 : (buf == 1 ? in1 : cst);
+        slots[sl] = src[idx];
+    }
+    __syncwarp();
+    const uint4 *rp = (const uint4 *)(prog + ((4 + 2 * (nin + nout) + 3) & ~3u)) + lane;
+    uint4 wq[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) wq[k] = (uint32_t)k < nr ? rp[32 * k] : make_uint4(0, 0, 0, 0);
+    for (uint32_t r = 0; r < nr; r += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint4 w = wq[k];
+            wq[k] = r + k + 4 < nr ? rp[32 * (r + k + 4)] : make_uint4(0, 0, 0, 0);
+            const uint32_t op = w.x >> 30;
+            if (__any_sync(0xffffffffu, op == 1)) {
+                if (op == 1) {
+                    fp x = slots[w.y & 1023], y = slots[(w.y >> 10) & 1023], t;
+                    fp_mul(t, x, y);
+                    slots[(w.x >> 20) & 1023] = t;
+                }
+            } else {
+                const uint32_t npos = op == 2 ? (w.x >> 17) & 7 : 0, nneg = op == 2 ? (w.x >> 14) & 7 : 0;
+                const uint32_t mp = __reduce_max_sync(0xffffffffu, npos), mn = __reduce_max_sync(0xffffffffu, nneg);
+                if (__any_sync(0xffffffffu, op == 2)) {
+                    const uint32_t t[7] = {w.y & 0x3fffu, (w.y >> 14) & 0x3fffu, w.z & 0x3fffu, (w.z >> 14) & 0x3fffu,
+                                           w.w & 0x3fffu, (w.w >> 14) & 0x3fffu, w.x & 0x3fffu};
+                    lin_acc A;
+                    lin_clear(A);
+#pragma unroll
+                    for (int j = 0; j < 7; j++)
+                        if ((uint32_t)j < mp) {                       // uniform: every lane walks the longest list of the round
+                            const uint32_t code = (uint32_t)j < npos ? t[j] : 0u;
+                            fp x = slots[code & 1023];
+                            lin_add_term(A.P, x, code >> 10);
+                        }
+#pragma unroll
+                    for (int j = 0; j < 7; j++)
+                        if ((uint32_t)j < mn) {
+                            const uint32_t code = (uint32_t)j < nneg ? t[6 - j] : 0u;
+                            fp x = slots[code & 1023];
+                            lin_add_term(A.N, x, code >> 10);
+                        }
+                    if (op == 2) {
+                        fp rr;
+                        lin_finish(rr, A);
+                        slots[(w.x >> 20) & 1023] = rr;
+                    }
+                }
+            }
+            if (STREAM && op == 0 && w.x) out0[w.z] = slots[w.y];   // a streamed output leaves its slot now
+            __syncwarp();
+        }
+    }
+    const uint32_t *op = prog + 4 + 2 * nin;
+    for (uint32_t e = lane; e < nout; e += 32) out0[op[2 * e + 1] & 0xffffffu] = slots[op[2 * e]];
+}
+__global__ void __launch_bounds__(32) k_fp_program2(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst, fp *out0,
+                                                    size_t s_in0, size_t s_in1, size_t s_out) {
+    fp_program2_body<false>(prog, in0, in1, cst, out0, s_in0, s_in1, s_out);
+}
+__global__ void __launch_bounds__(32) k_fp_program2_stream(const uint32_t *prog, const fp *in0, const fp *in1, const fp *cst,
+                                                           fp *out0, size_t s_in0, size_t s_in1, size_t s_out) {
+    fp_program2_body<true>(prog, in0, in1, cst, out0, s_in0, s_in1, s_out);
+}
+__global__ void __launch_bounds__(32) k_fp_program2_rows(const uint32_t *prog, const fp *in, const fp *cst, fp *out, unsigned m,
+                                                         size_t in_stride, size_t out_stride) {
+    const size_t j = blockIdx.x / m, g = blockIdx.x % m;
+    fp_program2_body<false>(prog, in + (j * in_stride + 8 * g) * 12, nullptr, cst, out + (j * out_stride + g) * 12, ~(size_t)0, 0, 0);
 }
 
 // Row-wise instances for the product trees of the GT product: block b = (row j, group g) of m groups per row reads the 8

@@ -35,7 +35,7 @@ struct msm_state {
     int sms = 148;                 // SM count of the device (B200: 148); set at context creation
     // window-group pipelining: the latency-bound tail of a group (combine, segment, tree, Horner) runs on this
     // higher-priority stream underneath the bucket accumulation of the next group
-    struct horner_prog { uint32_t *d = nullptr; int nslots = 0; };
+    struct horner_prog { uint32_t *d = nullptr; int nslots = 0, version = 1; };
     std::map<int, horner_prog> horner;      // window-Horner dataflow programs (fpprog.hpp), keyed by (nwin * 64 + c) * 2 + is_g2
     cudaStream_t tail = nullptr;
     cudaEvent_t ev_group[8] = {}, ev_done = nullptr;
@@ -595,6 +595,7 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
                         MCK(cudaMemcpyAsync(hp.d, P.words.data(), P.words.size() * 4, cudaMemcpyHostToDevice, s));
                         MCK(cudaStreamSynchronize(s));       // first use of this shape only: the host vector goes away
                         hp.nslots = P.nslots;
+                        hp.version = P.version;
                     }
                     st.horner[key] = hp;
                 }
@@ -602,7 +603,10 @@ static inline int msm_run(msm_state &st, const uint8_t *d_points, size_t pstride
                     fp *hom = (fp *)(st.buf + o_hom);
                     if constexpr (is_g1) k_msm_horner_prep<<<1, 128, 0, ts>>>(sg, nseg, nwin, hom);
                     else k_msm_horner_prep_g2<<<1, 128, 0, ts>>>(sg, nseg, nwin, hom);
-                    k_fp_program<<<1, 32, (size_t)hp.nslots * sizeof(fp), ts>>>(hp.d, hom, nullptr, nullptr, hom + per * nwin, 0, 0, 0);
+                    if (hp.version == 2)
+                        k_fp_program2<<<1, 32, (size_t)hp.nslots * sizeof(fp), ts>>>(hp.d, hom, nullptr, nullptr, hom + per * nwin, 0, 0, 0);
+                    else
+                        k_fp_program<<<1, 32, (size_t)hp.nslots * sizeof(fp), ts>>>(hp.d, hom, nullptr, nullptr, hom + per * nwin, 0, 0, 0);
                     if constexpr (is_g1) k_msm_horner_finish<<<1, 32, 0, ts>>>(hom + per * nwin, d_out_jac, d_out_aff);
                     else k_msm_horner_finish_g2<<<1, 32, 0, ts>>>(hom + per * nwin, d_out_jac, d_out_aff);
                     nl += 3;

@@ -10,6 +10,7 @@
 #include "../../nim_blscurve_b200/csrc/pairing.cuh"
 #include "../../nim_blscurve_b200/csrc/io.cuh"
 #include "../../nim_blscurve_b200/csrc/fpprog.hpp"
+#include "../../nim_blscurve_b200/csrc/fplin.cuh"
 using namespace bls;
 
 // subtractAll as blsgpu.cu: subtract_all arranges it: pairwise tree over (elems..., -dst), negated root, to affine
@@ -119,7 +120,44 @@ void hs_subtract_g1(g1_aff *dst, const g1_aff *p, size_t n) { hs_subtract<fp>(ds
 void hs_subtract_g2(g2_aff *dst, const g2_aff *p, size_t n) { hs_subtract<fp2>(dst, p, n); }
 
 // ---- fpprog.hpp: execute a compiled tail program on the CPU exactly as k_fp_program does on the device ----
-static void run_program(const std::vector<uint32_t> &w, const fp *in0, const fp *in1, const fp *cst, fp *out0) {
+// format 2 (rounds of products and rounds of linear combinations), exactly as k_fp_program2 does on the device: the
+// combinations go through the same lin_add_term / lin_finish of fplin.cuh
+static void run_program2(const std::vector<uint32_t> &w, const fp *in0, const fp *in1, const fp *cst, fp *out0) {
+    const uint32_t nr = w[0], nslots = w[1], nin = w[2], nout = w[3];
+    std::vector<fp> slots(nslots);
+    fp_set_zero(slots[0]);
+    for (uint32_t e = 0; e < nin; e++) {
+        uint32_t sl = w[4 + 2 * e], ref = w[5 + 2 * e], buf = ref >> 24, idx = ref & 0xffffffu;
+        slots[sl] = (buf == 0 ? in0 : (buf == 1 ? in1 : cst))[idx];
+    }
+    const uint32_t *rp = w.data() + ((4 + 2 * (nin + nout) + 3) & ~3u);
+    for (uint32_t r = 0; r < nr; r++, rp += 128) {
+        fp res[32];
+        bool wr[32];
+        for (int l = 0; l < 32; l++) {              // all lanes read before any lane writes (stricter than the device)
+            const uint32_t *x = rp + 4 * l;
+            const uint32_t op = x[0] >> 30;
+            wr[l] = false;
+            if (op == 1) { fp_mul(res[l], slots[x[1] & 1023], slots[(x[1] >> 10) & 1023]); wr[l] = true; }
+            else if (op == 2) {
+                const uint32_t npos = (x[0] >> 17) & 7, nneg = (x[0] >> 14) & 7;
+                const uint32_t t[7] = {x[1] & 0x3fffu, (x[1] >> 14) & 0x3fffu, x[2] & 0x3fffu, (x[2] >> 14) & 0x3fffu,
+                                       x[3] & 0x3fffu, (x[3] >> 14) & 0x3fffu, x[0] & 0x3fffu};
+                lin_acc A;
+                lin_clear(A);
+                for (uint32_t j = 0; j < npos; j++) lin_add_term(A.P, slots[t[j] & 1023], t[j] >> 10);
+                for (uint32_t j = 0; j < nneg; j++) lin_add_term(A.N, slots[t[6 - j] & 1023], t[6 - j] >> 10);
+                lin_finish(res[l], A);
+                wr[l] = true;
+            } else if (x[0]) out0[x[2]] = slots[x[1]];                                  // STORE
+        }
+        for (int l = 0; l < 32; l++) if (wr[l]) slots[(rp[4 * l] >> 20) & 1023] = res[l];
+    }
+    const uint32_t *op = w.data() + 4 + 2 * nin;
+    for (uint32_t e = 0; e < nout; e++) out0[op[2 * e + 1] & 0xffffffu] = slots[op[2 * e]];
+}
+
+static void run_program1(const std::vector<uint32_t> &w, const fp *in0, const fp *in1, const fp *cst, fp *out0) {
     const uint32_t nr = w[0], nslots = w[1], nin = w[2], nout = w[3];
     std::vector<fp> slots(nslots);
     fp_set_zero(slots[0]);
@@ -142,6 +180,12 @@ static void run_program(const std::vector<uint32_t> &w, const fp *in0, const fp 
     const uint32_t *op = w.data() + 4 + 2 * nin;
     for (uint32_t e = 0; e < nout; e++) out0[op[2 * e + 1] & 0xffffffu] = slots[op[2 * e]];
 }
+static void run_program(const std::vector<uint32_t> &w, const fp *in0, const fp *in1, const fp *cst, fp *out0) {
+    if (fpprog::program_format() == 2) run_program2(w, in0, in1, cst, out0); else run_program1(w, in0, in1, cst, out0);
+}
+// tests run every program in both formats
+extern "C" void hs_set_program_format(int f) { fpprog::g_format_override = f; }
+
 static void const_pool(fp *cst) {
     memcpy(cst + fpprog::CONST_FROB1, FROB1, sizeof(FROB1));
     memcpy(cst + fpprog::CONST_FROB2, FROB2, sizeof(FROB2));

@@ -416,3 +416,31 @@ def test_from_bytes_with_checks(hs, br):
             assert (err, bytes(o)) == (werr, wpt), (c.hex(), gc)
             seen.add(err)
     assert seen >= {0, 1, 2, 3}
+
+
+def test_programs_in_the_two_operand_format_too(hs):
+    """The programs are compiled to format 2 by default (rounds of products and rounds of linear combinations,
+    fpprog.hpp compile2 / fplin.cuh); format 1 (two-operand additions, BLSGPU_PROG_FORMAT=1) stays for A/B runs on the
+    device.  Every program test above runs again in format 1, and the flattening is checked to shorten the schedules."""
+    stats1, stats2 = (C.c_int * 4)(), (C.c_int * 4)()
+    rng = random.Random(5)
+
+    def rnd12():
+        return tuple(tuple((rng.randrange(P), rng.randrange(P)) for _ in range(3)) for _ in range(2))
+    part = buf(f12b(rnd12()))
+    r1, r2 = out(576), out(576)
+    hs.hs_set_program_format(1)
+    try:
+        assert hs.hs_prog_final_split(part, 1, r1, stats1) == 1
+        test_tail_programs(hs)
+        test_msm_horner_program(hs)
+        test_g2_programs(hs)
+        test_fp12_product_program(hs)
+        test_msm_horner_program_g2(hs)
+        test_miller_lines_program(hs)
+    finally:
+        hs.hs_set_program_format(0)
+    assert hs.hs_prog_final_split(part, 1, r2, stats2) == 1
+    assert bytes(r1) == bytes(r2)
+    assert stats2[0] < 1100 and stats1[0] > 2 * stats2[0], (list(stats1), list(stats2))   # 2 408 -> 973 rounds
+    assert stats2[1] == stats1[1]                                                           # same multiplication rounds
