@@ -55,6 +55,7 @@ struct blsgpu_ctx {
     bool ev_scratch_valid = false;
     cudaStream_t side2 = nullptr;                            // small batches: [r_i] pk_i beside both the hash and the signature work
     cudaStream_t side = nullptr;                             // the signature-side MSM runs beside the per-set stages
+    cudaStream_t chain = nullptr;                            // the RLC scalar chain (high priority, one SM-sized block)
     bool use_side = true;
     float stage_ms[ST_COUNT];
     int launches = 0;
@@ -148,6 +149,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2 * ST_COUNT + 4; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->chain) cudaStreamDestroy(ctx->chain);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -215,13 +217,15 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
         ctx->ev_valid[i] = true;
     }
-    // the side streams carry the scalar chain (a block that needs a whole SM to itself) and the signature-side sum:
-    // highest priority, so that when they become runnable together with a grid that fills the machine (the hash kernel
-    // behind a caller's H2D copy on the main stream) their blocks are placed first
+    // The scalar chain (ONE block that needs a whole SM to itself) has a stream of its own at the highest priority: when it
+    // becomes runnable together with a grid that fills the machine (the hash kernel behind a caller's H2D copy on the main
+    // stream) its block is placed first.  The signature-side sum that follows it stays at normal priority — at high
+    // priority its grids push the hash kernel's blocks back and the step gets 3 % longer (measured).
     int pri_lo = 0, pri_hi = 0;
     if (cudaDeviceGetStreamPriorityRange(&pri_lo, &pri_hi) != cudaSuccess) { cudaGetLastError(); pri_hi = 0; }
-    if ((e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, pri_hi)) != cudaSuccess) return bad("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithPriority(&ctx->side2, cudaStreamNonBlocking, pri_hi)) != cudaSuccess) return bad("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithPriority(&ctx->chain, cudaStreamNonBlocking, pri_hi)) != cudaSuccess) return bad("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking)) != cudaSuccess) return bad("cudaStreamCreate", e);
     if (getenv("BLSGPU_SIDE_STREAM")) ctx->use_side = atoi(getenv("BLSGPU_SIDE_STREAM")) != 0;
     if (getenv("BLSGPU_GRAPH")) ctx->use_graph = atoi(getenv("BLSGPU_GRAPH")) != 0;
     if ((e = cudaEventCreateWithFlags(&ctx->ev_share, cudaEventDisableTiming)) != cudaSuccess) return bad("cudaEventCreate", e);
@@ -596,6 +600,7 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
                        const uint8_t srb[32], uint32_t chunks, const uint64_t *scalars, int slot) {
     int rc = run_partial_impl(ctx, d_sets, n, first, total_n, srb, chunks, scalars, slot);
     if (rc) {
+        cudaStreamSynchronize(ctx->chain);
         cudaStreamSynchronize(ctx->side);
         cudaStreamSynchronize(ctx->side2);
         if (ctx->slices_ready) {
@@ -633,19 +638,25 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     // fork: the scalar chain (strictly sequential SHA-256 per reference chunk: tens of milliseconds for a large batch
     // when the caller passes tp.numThreads = 16..32 chunks) and the signature-side sum that consumes the scalars run on
     // a second stream, beside H(m_i), which needs neither; [r_i]pk_i waits for the scalars, the Miller loop for the sum
-    cudaStream_t g = ctx->use_side ? ctx->side : s;
+    cudaStream_t g = ctx->use_side ? ctx->side : s, cs = ctx->use_side ? ctx->chain : s;
     if (ctx->use_side) {
         CK(cudaEventRecord(ctx->ev[EV_FORK], s));
+        CK(cudaStreamWaitEvent(cs, ctx->ev[EV_FORK], 0));
         CK(cudaStreamWaitEvent(g, ctx->ev[EV_FORK], 0));
     }
-    BEGIN(ST_SCALARS, g);
-    int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars, g);
+    BEGIN(ST_SCALARS, cs);
+    int rc = launch_scalars(ctx, srb, n, first, total_n, chunks, scalars, cs);
     if (rc) return rc;
-    END(ST_SCALARS, g);
-    if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_SC], g));
+    END(ST_SCALARS, cs);
+    if (ctx->use_side) {
+        CK(cudaEventRecord(ctx->ev[EV_SC], cs));
+        CK(cudaStreamWaitEvent(g, ctx->ev[EV_SC], 0));
+    }
     // Small batches are latency chains (one thread per set): [r_i]pk_i does not depend on H(m_i), so it leads the
     // second stream instead of queueing behind the hash kernel.  Large batches fill the machine either way.
-    const bool g1_aside = ctx->use_side && n < 2048;
+    // measured (profiles/r2): beside the hash up to 8 192 sets (4 096 sets: 7.4 -> 6.7 ms); past that the two contend
+    static const size_t g1_aside_max = getenv("BLSGPU_G1_ASIDE_MAX") ? (size_t)atoll(getenv("BLSGPU_G1_ASIDE_MAX")) : 8192;
+    const bool g1_aside = ctx->use_side && n <= g1_aside_max;
     if (g1_aside) {
         cudaStream_t g1s = ctx->side2;
         CK(cudaStreamWaitEvent(g1s, ctx->ev[EV_SC], 0));
@@ -755,8 +766,15 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     BEGIN(ST_AFFINE, s);
     // small batches: one inversion per set is pure latency -> binary Euclid, one working lane per warp (it diverges
     // across the lanes of a warp: sharing warps it is no quicker than the uniform Fermat chain, 0.53 vs 0.46 ms at 129)
-    if (small) k_pairs_affine<<<(unsigned)n, 32, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 1, 1);
-    else k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 0, 0);
+    static const size_t aff_block_min = getenv("BLSGPU_AFFINE_BLOCK_MIN") ? (size_t)atoll(getenv("BLSGPU_AFFINE_BLOCK_MIN")) : 1025;
+    if (n >= aff_block_min) {
+        // one Euclid inversion per block of 128 threads, about 32 768 threads in flight: 1 set per thread up to 32 768
+        // sets, up to AFF_B beyond
+        int per = (int)((n + 32767) / 32768);
+        if (per > AFF_B) per = AFF_B;
+        k_pairs_affine<<<nblk((n + per - 1) / per), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 2, 0, per);
+    } else if (small) k_pairs_affine<<<(unsigned)n, 32, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 1, 1, AFF_B);
+    else k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 0, 0, AFF_B);
     END(ST_AFFINE, s);
     ctx->launches += 3;
     // Large batches behind long scalar chains (the caller's tp.numThreads = 16..32 chunks: tens of milliseconds of

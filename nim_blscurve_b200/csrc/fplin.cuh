@@ -32,6 +32,79 @@ BLS_FN void lin_add_term(uint64_t (&A)[12], const fp &x, uint32_t m) {
     for (int i = 0; i < 12; i++) A[i] += (uint64_t)x.l[i] * m;
 }
 
+#ifdef __CUDA_ARCH__
+// ---- device form: the same steps on hardware carry chains (a lone warp runs dependent instructions at one per ~4.5
+// cycles, so the count of chained instructions is the cost) ----
+#define BLS_R13(x) BLS_R12(x), "+r"(x[12])
+// acc (13 limbs) -= b
+BLS_FN void sub13(uint32_t *acc, const uint32_t *b) {
+    asm("sub.cc.u32 %0,%0,%13;\n\tsubc.cc.u32 %1,%1,%14;\n\tsubc.cc.u32 %2,%2,%15;\n\tsubc.cc.u32 %3,%3,%16;\n\t"
+        "subc.cc.u32 %4,%4,%17;\n\tsubc.cc.u32 %5,%5,%18;\n\tsubc.cc.u32 %6,%6,%19;\n\tsubc.cc.u32 %7,%7,%20;\n\t"
+        "subc.cc.u32 %8,%8,%21;\n\tsubc.cc.u32 %9,%9,%22;\n\tsubc.cc.u32 %10,%10,%23;\n\tsubc.cc.u32 %11,%11,%24;\n\t"
+        "subc.u32 %12,%12,%25;"
+        : BLS_R13(acc)
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]),
+          "r"(b[10]), "r"(b[11]), "r"(b[12]));
+}
+// acc (13 limbs) += 128 p
+BLS_FN void add_128p13(uint32_t *acc) {
+    asm("add.cc.u32 %0,%0,%13;\n\taddc.cc.u32 %1,%1,%14;\n\taddc.cc.u32 %2,%2,%15;\n\taddc.cc.u32 %3,%3,%16;\n\t"
+        "addc.cc.u32 %4,%4,%17;\n\taddc.cc.u32 %5,%5,%18;\n\taddc.cc.u32 %6,%6,%19;\n\taddc.cc.u32 %7,%7,%20;\n\t"
+        "addc.cc.u32 %8,%8,%21;\n\taddc.cc.u32 %9,%9,%22;\n\taddc.cc.u32 %10,%10,%23;\n\taddc.cc.u32 %11,%11,%24;\n\t"
+        "addc.u32 %12,%12,%25;"
+        : BLS_R13(acc)
+        : "n"(P128(0)), "n"(P128(1)), "n"(P128(2)), "n"(P128(3)), "n"(P128(4)), "n"(P128(5)), "n"(P128(6)), "n"(P128(7)),
+          "n"(P128(8)), "n"(P128(9)), "n"(P128(10)), "n"(P128(11)), "n"(P128(12)));
+}
+// 13 normalised limbs of sum_i A[i] 2^(32 i), A[i] < 2^40: low halves, plus the high halves one limb up
+BLS_FN void lin_norm13(uint32_t *o, const uint64_t (&A)[12]) {
+    uint32_t hi[12];
+    o[0] = (uint32_t)A[0];
+#pragma unroll
+    for (int i = 1; i < 12; i++) o[i] = (uint32_t)A[i];
+    o[12] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) hi[i] = (uint32_t)(A[i] >> 32);
+    add12(o + 1, hi);                                        // no carry out: the top limb is hi[11] + carry < 2^9
+}
+// t < 4p (12 limbs) -> t mod p
+BLS_FN void reduce_4p12(uint32_t *r, const uint32_t *t) {
+    uint32_t u[12], v[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) u[i] = t[i];
+    uint32_t bw;
+    // u = t - 2p
+    asm("sub.cc.u32 %0,%0,%13;\n\tsubc.cc.u32 %1,%1,%14;\n\tsubc.cc.u32 %2,%2,%15;\n\tsubc.cc.u32 %3,%3,%16;\n\t"
+        "subc.cc.u32 %4,%4,%17;\n\tsubc.cc.u32 %5,%5,%18;\n\tsubc.cc.u32 %6,%6,%19;\n\tsubc.cc.u32 %7,%7,%20;\n\t"
+        "subc.cc.u32 %8,%8,%21;\n\tsubc.cc.u32 %9,%9,%22;\n\tsubc.cc.u32 %10,%10,%23;\n\tsubc.cc.u32 %11,%11,%24;\n\t"
+        "subc.u32 %12,0,0;"
+        : BLS_R12(u), "=r"(bw)
+        : "n"(P32(0) << 1), "n"((P32(1) << 1) | (P32(0) >> 31)), "n"((P32(2) << 1) | (P32(1) >> 31)),
+          "n"((P32(3) << 1) | (P32(2) >> 31)), "n"((P32(4) << 1) | (P32(3) >> 31)), "n"((P32(5) << 1) | (P32(4) >> 31)),
+          "n"((P32(6) << 1) | (P32(5) >> 31)), "n"((P32(7) << 1) | (P32(6) >> 31)), "n"((P32(8) << 1) | (P32(7) >> 31)),
+          "n"((P32(9) << 1) | (P32(8) >> 31)), "n"((P32(10) << 1) | (P32(9) >> 31)), "n"((P32(11) << 1) | (P32(10) >> 31)));
+#pragma unroll
+    for (int i = 0; i < 12; i++) v[i] = bw ? t[i] : u[i];    // < 2p
+    reduce_once12(r, v);
+}
+BLS_FN void lin_finish(fp &r, const lin_acc &a) {
+    uint32_t D[13], T[13];
+    lin_norm13(D, a.P);
+    lin_norm13(T, a.N);
+    add_128p13(D);
+    sub13(D, T);                                             // D = P - N + 128 p in (0, 233 p)
+    // quotient estimate from the top 21 bits: h = D >> 368, p >> 368 = 6657; h / 6658 as a multiply-high never overshoots
+    // D / p and undershoots by at most 2
+    const uint32_t h = (D[12] << 16) | (D[11] >> 16);
+    const uint32_t q = __umulhi(h, 1321131424u) >> 11;       // floor(2^43 / 6658) = 1321131424
+    uint64_t qp[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) qp[i] = (uint64_t)P32(i) * q;
+    lin_norm13(T, qp);
+    sub13(D, T);                                             // in [0, 4p): twelve limbs
+    reduce_4p12(r.l, D);
+}
+#else
 // r = (P - N) mod p, fully reduced.  Requires sum of magnitudes on each side <= 120 (N < 128 p keeps D positive,
 // D < 248 p < 2^389 keeps the quotient below 256).
 BLS_FN void lin_finish(fp &r, const lin_acc &a) {
@@ -77,5 +150,6 @@ BLS_FN void lin_finish(fp &r, const lin_acc &a) {
 #pragma unroll
     for (int i = 0; i < 12; i++) r.l[i] = R[i];
 }
+#endif
 
 }  // namespace bls

@@ -266,12 +266,16 @@ struct Program {
 //         the negative ones:    slot[dst] = sum_pos mag * slot - sum_neg mag * slot   (mod p; fplin.cuh)
 //   STORE w1 = source slot, w2 = OUT0 index                 (streamed outputs)
 enum { LIN_MAXT = 7, LIN_MAXMAG = 15 };
-// programs are compiled to format 2 unless BLSGPU_PROG_FORMAT=1 (A/B runs) or a test overrides it
+// Programs are compiled to format 1 unless BLSGPU_PROG_FORMAT=2 (A/B runs) or a test overrides it.  Measured on B200
+// (profiles/r2/r2_summary.md): format 2 cuts the final exponentiation from 2 408 to 973 rounds, but a combination round
+// costs a lone warp 1.35 us (accumulate + carry passes + quotient step are ~360 dependent instructions at ~4.5 cycles
+// each) against 0.22 us for a two-operand round, so the shorter schedule runs SLOWER (final exponentiation 1.12 ms
+// against 0.96 ms).  Kept as a tested alternative, not the default.
 static thread_local int g_format_override = 0;
 inline int program_format() {
     if (g_format_override) return g_format_override;
-    static const int f = getenv("BLSGPU_PROG_FORMAT") ? atoi(getenv("BLSGPU_PROG_FORMAT")) : 2;
-    return f == 1 ? 1 : 2;
+    static const int f = getenv("BLSGPU_PROG_FORMAT") ? atoi(getenv("BLSGPU_PROG_FORMAT")) : 1;
+    return f == 2 ? 2 : 1;
 }
 
 inline uint32_t enc(int op, int d, int a, int b) { return ((uint32_t)op << 30) | ((uint32_t)d << 20) | ((uint32_t)a << 10) | (uint32_t)b; }
