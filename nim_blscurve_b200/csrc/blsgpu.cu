@@ -414,13 +414,13 @@ static size_t small_route_max() {
     return v > SMALL_ROUTE_CAP ? SMALL_ROUTE_CAP : v;
 }
 static size_t small_lines_max() {
-    static const size_t v = getenv("BLSGPU_SMALL_LINES_MAX") ? (size_t)atoll(getenv("BLSGPU_SMALL_LINES_MAX")) : 2049;
+    static const size_t v = getenv("BLSGPU_SMALL_LINES_MAX") ? (size_t)atoll(getenv("BLSGPU_SMALL_LINES_MAX")) : 1025;
     return v > 16385 ? 16385 : v;
 }
 #define SMALL_ROUTE_MAX SMALL_ROUTE_CAP   /* buffer strides */
 // Mid-size route: two lanes per set for H(m_i) and the line evaluations (fp2h.cuh) while a thread per set leaves the
 // machine under-filled: 148 SMs x 512 resident threads = 75 776 lanes, i.e. up to ~38k sets in one wave of lane pairs.
-static size_t pair_hash_min() { static const size_t v = getenv("BLSGPU_PAIR_HASH_MIN") ? (size_t)atoll(getenv("BLSGPU_PAIR_HASH_MIN")) : 1025; return v; }
+static size_t pair_hash_min() { static const size_t v = getenv("BLSGPU_PAIR_HASH_MIN") ? (size_t)atoll(getenv("BLSGPU_PAIR_HASH_MIN")) : 2049; return v; }
 static size_t pair_hash_max() { static const size_t v = getenv("BLSGPU_PAIR_HASH_MAX") ? (size_t)atoll(getenv("BLSGPU_PAIR_HASH_MAX")) : 40000; return v; }
 static size_t pair_lines_max() { static const size_t v = getenv("BLSGPU_PAIR_LINES_MAX") ? (size_t)atoll(getenv("BLSGPU_PAIR_LINES_MAX")) : 40000; return v; }
 #define SMALL_FP_PER_SET (6 + 6 + 6 + 6 + 64)

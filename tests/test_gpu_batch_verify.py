@@ -271,3 +271,26 @@ def test_error_convention_of_the_c_abi(br, srb):
     assert L.blsgpu_batch_verify(h, sets, 16, srb, 4, None, gt) == 1
     assert (True, bytes(gt)) == br.batch_verify(sets[:16 * 320], srb, 4)
     L.blsgpu_destroy(h)
+
+
+def test_graph_replay_follows_the_random_bytes(br):
+    """Small batches replay a captured CUDA graph from the third call with the same (buffer, n, chunks) on
+    (blsgpu.cu verify_graphed); the 32 random bytes are the one input that changes between replays and reach the scalar
+    kernel through device memory.  A failing batch's GT depends on every scalar, so it must follow BLST's for each new
+    secureRandomBytes — direct call, capture call and replays alike — and a corrupted copy in the same buffer must be seen."""
+    import nim_blscurve_b200 as bg
+    c = bg.BatchedBLSVerifierCache(max_sets=64, device=0)
+    try:
+        sets = bytearray(br.make_sets(0, 33))
+        sets[5 * 320 + 128:6 * 320] = sets[6 * 320 + 128:7 * 320]       # wrong signature on set 5
+        sets = bytes(sets)
+        for k in range(6):
+            srb_k = hashlib.sha256(b"replay %d" % k).digest()
+            assert c.verify_raw(sets, srb_k, 4, want_gt=True) == br.batch_verify(sets, srb_k, 4), k
+        good = br.make_sets(100, 33)
+        for k in range(3):
+            srb_k = hashlib.sha256(b"valid %d" % k).digest()
+            assert c.verify_raw(good, srb_k, 4) is True
+            assert c.verify_raw(sets, srb_k, 4) is False
+    finally:
+        c.close()
