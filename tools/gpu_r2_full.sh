@@ -1,3 +1,4 @@
+# Full one-GPU validation: GPU test suite, host-buffer probe, stage probe, bench line.  usage: bash tools/gpu_r2_full.sh <outdir>
 set -x
 out=gpurun_out/${1:-g4}; mkdir -p $out
 timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log

@@ -1,3 +1,4 @@
+# Batch-size sweep with stage times (default thresholds, and [r_i]pk_i kept on the main stream) after the GPU suite.
 set -x
 out=gpurun_out/${1:-g9}; mkdir -p $out
 timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log
