@@ -54,11 +54,20 @@ def _pack(sets) -> bytes:
 class BatchedBLSVerifierCache:
     """Device scratch for batch verification (replaces the per-thread pairing contexts, :62-69)."""
 
-    def __init__(self, max_sets: int = 1 << 14, device: int = 0, numThreads: int = 1):
+    def __init__(self, max_sets: int = 1 << 14, device: int = 0, numThreads: int = 1,
+                 devices: Optional[Sequence[int]] = None):
+        """devices: several GPUs behind ONE cache (blsgpu_create_multi): batch verification and the MSMs are cut over
+        them inside the call, replacing the Taskpools fan-out of bls_batch_verifier.nim:316-369."""
         L = lib()
         if L.blsgpu_device_count() <= 0:
             raise BlsGpuError("no CUDA device visible: nim_blscurve_b200 has no CPU fallback")
-        self._h = L.blsgpu_create(device, max_sets)
+        self.devices = list(devices) if devices else None
+        if self.devices:
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            self._h = L.blsgpu_create_multi(arr, len(self.devices), max_sets)
+            device = self.devices[0]
+        else:
+            self._h = L.blsgpu_create(device, max_sets)
         if not self._h:
             raise BlsGpuError(L.blsgpu_last_error(None).decode())
         self.numThreads = numThreads
@@ -92,9 +101,9 @@ class BatchedBLSVerifierCache:
     # ---- raw calls -------------------------------------------------------------------------
     def _ensure(self, n):
         if n > self.capacity():
-            dev = self.device
+            dev, devs = self.device, self.devices
             self.close()
-            self.__init__(max_sets=max(n, 1), device=dev, numThreads=self.numThreads)
+            self.__init__(max_sets=max(n, 1), device=dev, numThreads=self.numThreads, devices=devs)
 
     def verify_raw(self, sets: bytes, srb: bytes, chunks: int, scalars: Optional[Sequence[int]] = None,
                    want_gt: bool = False):

@@ -52,3 +52,20 @@ def test_multi_context_matches_blst(br, srb):
                 assert (bool(rc), bytes(gt)) == br.batch_verify(s, srb, chunks)
     finally:
         L.blsgpu_destroy(h)
+
+
+def test_python_mirror_multi_device_cache(br, srb):
+    """BatchedBLSVerifierCache(devices=[...]): the mirror of the shim's -d:blsgpuNumDevices, growing on demand."""
+    import nim_blscurve_b200 as bg
+    ndev = bg.lib().blsgpu_device_count()
+    cache = bg.BatchedBLSVerifierCache(max_sets=8, devices=[k % ndev for k in range(2)])
+    try:
+        sets = br.make_sets(0, 40)                            # past the initial capacity: the context is re-created
+        tp = bg.Taskpool.new(4)
+        assert bg.batchVerify(tp, cache, sets, srb) is True
+        bad = bytearray(sets)
+        bad[7 * 320 + 96] ^= 1
+        assert cache.verify_raw(bytes(bad), srb, 4, want_gt=True) == br.batch_verify(bytes(bad), srb, 4)
+        assert bg.lib().blsgpu_device_span(cache.handle) == 2
+    finally:
+        cache.close()
