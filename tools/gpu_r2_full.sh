@@ -15,3 +15,4 @@ print(d['block_batch']['ms'], d['config1']['chunks_4'], d['msm_g1']['value'])
 print({k:round(v['ms'],2) for k,v in d['batch_sizes'].items()})
 print({k:round(v['ms'],2) for k,v in d['chunk_sweep']['by_rlc_chunks'].items()})
 PY
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
