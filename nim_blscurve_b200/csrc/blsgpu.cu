@@ -76,6 +76,7 @@ struct blsgpu_ctx {
     cudaStream_t copy_stream = nullptr, slice_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_copy[4], ev_slice[4];
     bool slices_ready = false;
+    bool chain_hogged = false;                               // the last scalar launch reserved an SM (k_wait_started applies)
     bool chain_smem_raised = false;                          // k_rlc_scalars allowed to reserve a whole SM's shared memory
     // multi-device context (blsgpu_create_multi): this context is the leader (share 0 + the one final exponentiation),
     // peers[k-1] owns share k on its own device; the 576-byte partials and the flags are gathered into the leader
@@ -327,12 +328,15 @@ static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size
             ctx->chain_smem_raised = true;
         }
     }
+    // d_flags[3]: "the block of chains is resident" (cleared with the other flags at the start of the call)
+    volatile int *started = hog && ctx->use_side ? ctx->d_flags + 3 : nullptr;
+    ctx->chain_hogged = started != nullptr;
     if (ctx->srb_from_dev) {
         // h_pinned + 1024: 8 big-endian words written by the caller of the captured sequence before every launch
         CK(cudaMemcpyAsync(ctx->d_srb, ctx->h_pinned + 1024, 32, cudaMemcpyHostToDevice, s));
-        k_rlc_scalars<<<nblk(nb, 32), 32, hog, s>>>(words8(), ctx->d_srb, total_n, chunks, first, n, ctx->d_r);
+        k_rlc_scalars<<<nblk(nb, 32), 32, hog, s>>>(words8(), ctx->d_srb, total_n, chunks, first, n, ctx->d_r, started);
     } else {
-        k_rlc_scalars<<<nblk(nb, 32), 32, hog, s>>>(words_of(srb), nullptr, total_n, chunks, first, n, ctx->d_r);
+        k_rlc_scalars<<<nblk(nb, 32), 32, hog, s>>>(words_of(srb), nullptr, total_n, chunks, first, n, ctx->d_r, started);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -651,6 +655,13 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     if (ctx->use_side) {
         CK(cudaEventRecord(ctx->ev[EV_SC], cs));
         CK(cudaStreamWaitEvent(g, ctx->ev[EV_SC], 0));
+    }
+    static const int chain_wait = getenv("BLSGPU_CHAIN_WAIT") ? atoi(getenv("BLSGPU_CHAIN_WAIT")) : 1;
+    if (chain_wait && ctx->chain_hogged && !scalars) {
+        // the main stream (whose next kernel fills the machine) waits until the chains' block is placed: ~10 us when the
+        // device is idle, at most 0.2 ms (400 000 cycles) when it is not
+        k_wait_started<<<1, 32, 0, s>>>(ctx->d_flags + 3, 400000);
+        ctx->launches++;
     }
     // Small batches are latency chains (one thread per set): [r_i]pk_i does not depend on H(m_i), so it leads the
     // second stream instead of queueing behind the hash kernel.  Large batches fill the machine either way.

@@ -68,8 +68,11 @@ __device__ __forceinline__ void chunk_range(size_t nchunks, size_t total, size_t
 // the indices this rank owns ([first, first+n) of the global batch).
 // d_srb (nullable): the 32 random bytes as 8 big-endian words in device memory instead of the by-value copy — the
 // form a captured CUDA graph needs, where kernel arguments are frozen but the bytes change with every call.
+// started (nullable): set to 1 by the first thread as soon as the block runs (k_wait_started on the main stream holds the
+// hash kernel back until then, so that the block of chains gets its SM before the machine is full).
 __global__ void k_rlc_scalars(words8 srb, const uint32_t *d_srb, size_t total_n, uint32_t chunks, size_t first, size_t n,
-                              uint64_t *out) {
+                              uint64_t *out, volatile int *started) {
+    if (started && blockIdx.x == 0 && threadIdx.x == 0) { *started = 1; __threadfence(); }
     if (d_srb) for (int k = 0; k < 8; k++) srb.w[k] = d_srb[k];
     size_t nb = chunks == 0 ? 1 : (total_n < chunks ? total_n : (size_t)chunks);
     size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,6 +106,14 @@ __global__ void k_rlc_scalars(words8 srb, const uint32_t *d_srb, size_t total_n,
         } while (r == 0);
         if (i >= first && i < first + n) out[i - first] = r;
     }
+}
+
+// One thread polls the flag the chain kernel raises when its block is resident; gives up after `budget` clock cycles
+// (the chain may be queued behind other work on a busy device: then the hash simply goes first, as without this).
+__global__ void k_wait_started(volatile int *started, long long budget) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const long long t0 = clock64();
+    while (*started == 0 && clock64() - t0 < budget) __nanosleep(200);
 }
 
 // Blinding scalars of MultiSignatureSet.combine (blst_min_pubkey_sig_core.nim:590-606): seed <- SHA256(seed), the
