@@ -51,6 +51,10 @@ struct blsgpu_ctx {
     uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
     cudaEvent_t ev[2 * ST_COUNT + 4];                        // stage begin/end pairs + fork/join/G1-ready
     bool ev_valid[2 * ST_COUNT + 4];
+    // buffers of the one-pair Miller loop of (S, -G1) when it runs on the side stream beside the big loop (run_partial_impl)
+    uint32_t *sig_lines = nullptr;
+    fp12 *sig_F = nullptr, *sig_F2 = nullptr, *sig_seg = nullptr;
+    fp *sig_small_lines = nullptr;
     cudaEvent_t ev_scratch[8];                               // event window of the deferred signature-pair Miller loop
     bool ev_scratch_valid = false;
     cudaStream_t side2 = nullptr;                            // small batches: [r_i] pk_i beside both the hash and the signature work
@@ -130,6 +134,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     ctx->peers.clear();
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_gather); cudaFree(ctx->d_gather_flags); cudaFree(ctx->d_srb);
+    cudaFree(ctx->sig_lines); cudaFree(ctx->sig_F); cudaFree(ctx->sig_F2); cudaFree(ctx->sig_seg); cudaFree(ctx->sig_small_lines);
     for (auto &g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->ev_share) cudaEventDestroy(ctx->ev_share);
     if (ctx->slices_ready) {
@@ -751,6 +756,41 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     k_sig_pair<<<1, 32, 0, g>>>(ctx->d_S, n, ctx->d_Q, ctx->d_P);
     ctx->launches++;
     END(ST_G2SUM, g);
+    // From 8 192 sets on the n set pairs do not wait for the signature sum (scalar chain, then the signature-side MSM: 4 ms
+    // at 8 192 sets, tens of milliseconds behind the long chains of a large batch).  Pair number n = (S, -G1) gets its own
+    // one-pair Miller loop right here on the side stream, with buffers of its own, beside the big loop of the main stream;
+    // after the join the two values are multiplied (one Fp12 product program).  Same product of the same n + 1 Miller
+    // values, hence same GT.  Measured: 8 192 sets 8.10 -> 7.24 ms, 16 384: 11.1 -> 10.5, 32 768: 18.05 -> 17.2,
+    // 131 072: 57.7 -> 57.0; below 8 192 the extra loop costs more than the wait it removes (4 096: 6.5 -> 6.9 ms).
+    static const size_t defer_min = getenv("BLSGPU_DEFER_SIG_MIN") ? (size_t)atoll(getenv("BLSGPU_DEFER_SIG_MIN")) : 8192;
+    const bool defer_sig = ctx->use_side && !ctx->serial_tail && n >= defer_min && !scalars;
+    if (defer_sig) {
+        const size_t per = (size_t)ML_NLINES * 6;
+        if (!ctx->sig_lines) {
+            CK(cudaMalloc((void **)&ctx->sig_lines, (size_t)ML_NLINES * ML_LINE_WORDS * 4 * 32));
+            CK(cudaMalloc((void **)&ctx->sig_F, 2048 * sizeof(fp12)));
+            CK(cudaMalloc((void **)&ctx->sig_F2, 512 * sizeof(fp12)));
+            CK(cudaMalloc((void **)&ctx->sig_seg, 64 * sizeof(fp12)));
+            CK(cudaMalloc((void **)&ctx->sig_small_lines, 2 * per * sizeof(fp)));
+        }
+        // run_miller works on the context's buffers and stream: lend it the pair's own for this one call
+        struct swap_t {
+            blsgpu_ctx *c; uint32_t *lines; size_t lines_cap, f_cap, f2_cap; fp12 *F, *F2, *seg; fp *sl; cudaStream_t st; cudaEvent_t ev[8];
+            ~swap_t() {
+                c->d_lines = lines; c->lines_cap = lines_cap; c->f_cap = f_cap; c->f2_cap = f2_cap; c->d_F = F; c->d_F2 = F2;
+                c->d_seg = seg; c->d_small_lines = sl; c->stream = st;
+                const int ids[4] = {ST_LINES, ST_ACC, ST_GTPROD, ST_PARTIAL};
+                for (int k = 0; k < 4; k++) { c->ev[2 * ids[k]] = ev[2 * k]; c->ev[2 * ids[k] + 1] = ev[2 * k + 1]; }
+            }
+        } keep{ctx, ctx->d_lines, ctx->lines_cap, ctx->f_cap, ctx->f2_cap, ctx->d_F, ctx->d_F2, ctx->d_seg, ctx->d_small_lines, ctx->stream, {}};
+        const int ids[4] = {ST_LINES, ST_ACC, ST_GTPROD, ST_PARTIAL};
+        for (int k = 0; k < 4; k++) { keep.ev[2 * k] = ctx->ev[2 * ids[k]]; keep.ev[2 * k + 1] = ctx->ev[2 * ids[k] + 1]; }
+        for (int k = 0; k < 4; k++) { ctx->ev[2 * ids[k]] = ctx->ev_scratch[2 * k]; ctx->ev[2 * ids[k] + 1] = ctx->ev_scratch[2 * k + 1]; }
+        ctx->d_lines = ctx->sig_lines; ctx->lines_cap = 32; ctx->d_F = ctx->sig_F; ctx->f_cap = 2048; ctx->d_F2 = ctx->sig_F2;
+        ctx->f2_cap = 512; ctx->d_seg = ctx->sig_seg; ctx->d_small_lines = ctx->sig_small_lines; ctx->stream = g;
+        rc = run_miller(ctx, 1, slot + 1, n);
+        if (rc) return rc;
+    }
     if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_JOIN], g));
     if (!sliced) BEGIN(ST_HASH, s);
     if (sliced) {
@@ -788,28 +828,13 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     else k_pairs_affine<<<nblk((n + AFF_B - 1) / AFF_B), 128, 0, s>>>(ctx->d_H, ctx->d_Pj, n, ctx->d_Q, ctx->d_P, 0, 0, AFF_B);
     END(ST_AFFINE, s);
     ctx->launches += 3;
-    // Large batches behind long scalar chains (the caller's tp.numThreads = 16..32 chunks: tens of milliseconds of
-    // sequential SHA-256, then the signature-side MSM): the n set pairs do not wait for the signature sum.  Their
-    // multi-Miller loop runs first; pair number n = (S, -G1) gets its own small Miller loop after the join and the two
-    // values are multiplied (one Fp12 product program).  Same product of the same n + 1 Miller values, hence same GT.
-    static const size_t defer_min = getenv("BLSGPU_DEFER_SIG_MIN") ? (size_t)atoll(getenv("BLSGPU_DEFER_SIG_MIN")) : 16384;
-    const size_t nchunks = chunks == 0 ? 1 : (total_n < chunks ? total_n : (size_t)chunks);
-    const bool defer_sig = ctx->use_side && !ctx->serial_tail && n >= defer_min && !scalars && total_n / nchunks >= 2048;
     if (!defer_sig) {
         if (ctx->use_side) CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));   // join: pair number n is in place
         return run_miller(ctx, n + 1, slot);
     }
-    rc = run_miller(ctx, n, slot);
+    rc = run_miller(ctx, n, slot);                           // the n set pairs; (S, -G1) is being done on the side stream
     if (rc) return rc;
     CK(cudaStreamWaitEvent(s, ctx->ev[EV_JOIN], 0));
-    // the events of the big loop must survive for the stage report: run the one-pair loop with its own event window
-    cudaEvent_t saved[8];
-    const int ids[4] = {ST_LINES, ST_ACC, ST_GTPROD, ST_PARTIAL};
-    for (int k = 0; k < 4; k++) { saved[2 * k] = ctx->ev[2 * ids[k]]; saved[2 * k + 1] = ctx->ev[2 * ids[k] + 1]; }
-    for (int k = 0; k < 4; k++) { ctx->ev[2 * ids[k]] = ctx->ev_scratch[2 * k]; ctx->ev[2 * ids[k] + 1] = ctx->ev_scratch[2 * k + 1]; }
-    rc = run_miller(ctx, 1, slot + 1, n);
-    for (int k = 0; k < 4; k++) { ctx->ev[2 * ids[k]] = saved[2 * k]; ctx->ev[2 * ids[k] + 1] = saved[2 * k + 1]; }
-    if (rc) return rc;
     blsgpu_ctx::dev_prog p2;
     rc = get_prog(ctx, 4, 2, p2);
     if (rc) return rc;

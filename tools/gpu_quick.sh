@@ -1,4 +1,5 @@
-for i in 1 2; do
-echo "== wait on"; python tools/probe.py --chunks 16 16384 32768 65536 131072 2>&1 | grep "^n=" | cut -c1-210
-echo "== wait off"; BLSGPU_CHAIN_WAIT=0 python tools/probe.py --chunks 16 16384 32768 65536 131072 2>&1 | grep "^n=" | cut -c1-210
+for m in 16384 2048; do
+echo "== defer_min=$m"
+BLSGPU_DEFER_SIG_MIN=$m python tools/probe.py --chunks 16 2048 4096 8192 16384 32768 2>&1 | grep "^n=" | cut -c1-215
 done
+BLSGPU_DEFER_SIG_MIN=2048 python -m pytest tests/test_gpu_golden_and_shares.py -m gpu -x -q 2>&1 | tail -2
