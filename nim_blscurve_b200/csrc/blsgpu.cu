@@ -45,12 +45,13 @@ struct blsgpu_ctx {
     fp12 *d_partials = nullptr;   // 64 slots
     uint8_t *d_gtb = nullptr;     // 576 canonical GT bytes
     int *d_flags = nullptr;       // [0] pk infinity, [1] is_one
+    unsigned long long *d_dbg = nullptr;                     // BLSGPU_DEBUG_CHAIN: timestamps of the scalar chain
     void *d_misc = nullptr;       // scratch for aggregate / hash API
     size_t misc_bytes = 0;
     void *d_misc2 = nullptr;      // small result scratch (MSM output)
     uint8_t *h_pinned = nullptr;  // 4 KiB pinned for small D2H results
-    cudaEvent_t ev[2 * ST_COUNT + 4];                        // stage begin/end pairs + fork/join/G1-ready
-    bool ev_valid[2 * ST_COUNT + 4];
+    cudaEvent_t ev[2 * ST_COUNT + 5];                        // stage begin/end pairs + fork/join/G1-ready
+    bool ev_valid[2 * ST_COUNT + 5];
     // buffers of the one-pair Miller loop of (S, -G1) when it runs on the side stream beside the big loop (run_partial_impl)
     uint32_t *sig_lines = nullptr;
     fp12 *sig_F = nullptr, *sig_F2 = nullptr, *sig_seg = nullptr;
@@ -144,7 +145,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     if (ctx->ev_scratch_valid) for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev_scratch[i]);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_r); cudaFree(ctx->d_H); cudaFree(ctx->d_Pj); cudaFree(ctx->d_Q);
     cudaFree(ctx->d_P); cudaFree(ctx->d_S); cudaFree(ctx->d_F); cudaFree(ctx->d_partials); cudaFree(ctx->d_gtb);
-    cudaFree(ctx->d_flags); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_consts); cudaFree(ctx->d_gt);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_dbg); cudaFree(ctx->d_misc); cudaFree(ctx->d_misc2); cudaFree(ctx->d_consts); cudaFree(ctx->d_gt);
     for (auto &kv : ctx->combine_progs) cudaFree(kv.second.d);
     for (auto &kv : ctx->final_progs) cudaFree(kv.second.d);
     for (auto &kv : ctx->norm_progs) cudaFree(kv.second.d);
@@ -153,7 +154,7 @@ extern "C" void blsgpu_destroy(blsgpu_ctx *ctx) {
     cudaFree(ctx->d_norm); cudaFree(ctx->d_small); cudaFree(ctx->d_small_lines); cudaFree(ctx->d_seg); cudaFree(ctx->d_lines); cudaFree(ctx->d_F2);
     msm_free(ctx->msm);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (int i = 0; i < 2 * ST_COUNT + 4; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2 * ST_COUNT + 5; i++) if (ctx->ev_valid[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->chain) cudaStreamDestroy(ctx->chain);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
@@ -169,7 +170,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     blsgpu_ctx *ctx = new blsgpu_ctx();
     ctx->device = device;
     ctx->cap = max_sets;
-    for (int i = 0; i < 2 * ST_COUNT + 4; i++) ctx->ev_valid[i] = false;
+    for (int i = 0; i < 2 * ST_COUNT + 5; i++) ctx->ev_valid[i] = false;
     for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.f;
     cudaError_t e = cudaSetDevice(device);
     auto bad = [&](const char *what, cudaError_t err) {
@@ -204,6 +205,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     ALLOC(ctx->d_consts, fpprog::CONST_COUNT * sizeof(fp));
     ALLOC(ctx->d_norm, 2 * sizeof(fp));
     ALLOC(ctx->d_flags, 4 * sizeof(int));
+    if (getenv("BLSGPU_DEBUG_CHAIN")) ALLOC(ctx->d_dbg, 8 * sizeof(unsigned long long));
     ALLOC(ctx->d_srb, 32);
 #undef ALLOC
     if ((e = cudaMallocHost((void **)&ctx->h_pinned, 4096)) != cudaSuccess) return bad("cudaMallocHost", e);
@@ -219,7 +221,7 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bad("cudaDeviceSynchronize", e);
     ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
     if (getenv("BLSGPU_ACC_TEAM")) ctx->acc_team = atoi(getenv("BLSGPU_ACC_TEAM")) != 0;
-    for (int i = 0; i < 2 * ST_COUNT + 4; i++) {
+    for (int i = 0; i < 2 * ST_COUNT + 5; i++) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bad("cudaEventCreate", e);
         ctx->ev_valid[i] = true;
     }
@@ -309,6 +311,7 @@ static words8 words_of(const uint8_t b[32]) {
 #define EV_JOIN (2 * ST_COUNT + 1)
 #define EV_G1 (2 * ST_COUNT + 2)
 #define EV_SC (2 * ST_COUNT + 3)
+#define EV_HASHED (2 * ST_COUNT + 4)
 
 // scalars for global indices [first, first+n) into d_r
 static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size_t first, size_t total_n,
@@ -336,13 +339,21 @@ static int launch_scalars(blsgpu_ctx *ctx, const uint8_t srb[32], size_t n, size
     // d_flags[3]: "the block of chains is resident" (cleared with the other flags at the start of the call)
     volatile int *started = hog && ctx->use_side ? ctx->d_flags + 3 : nullptr;
     ctx->chain_hogged = started != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nblk(nb, 32));
+    cfg.blockDim = dim3(32);
+    cfg.dynamicSmemBytes = hog;
+    cfg.stream = s;
+    const uint32_t *d_srb = nullptr;
+    words8 w8 = words8();
     if (ctx->srb_from_dev) {
         // h_pinned + 1024: 8 big-endian words written by the caller of the captured sequence before every launch
         CK(cudaMemcpyAsync(ctx->d_srb, ctx->h_pinned + 1024, 32, cudaMemcpyHostToDevice, s));
-        k_rlc_scalars<<<nblk(nb, 32), 32, hog, s>>>(words8(), ctx->d_srb, total_n, chunks, first, n, ctx->d_r, started);
+        d_srb = ctx->d_srb;
     } else {
-        k_rlc_scalars<<<nblk(nb, 32), 32, hog, s>>>(words_of(srb), nullptr, total_n, chunks, first, n, ctx->d_r, started);
+        w8 = words_of(srb);
     }
+    CK(cudaLaunchKernelEx(&cfg, k_rlc_scalars, w8, d_srb, total_n, chunks, first, n, ctx->d_r, started, ctx->d_dbg));
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -619,6 +630,14 @@ static int run_partial(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t f
         cudaStreamSynchronize(ctx->stream);
         cudaGetLastError();
     }
+    if (!rc && ctx->d_dbg) {                                  // BLSGPU_DEBUG_CHAIN: when did the chain block start / end
+        unsigned long long h[8];
+        cudaStreamSynchronize(ctx->chain);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[blsgpu chain] n=%zu start->end %.3f ms, wait exit - chain start %.3f ms, sm %llu, seen %llu\n", n,
+                (double)(h[1] - h[0]) * 1e-6, ((double)h[2] - (double)h[0]) * 1e-6, h[3], h[4]);
+    }
     return rc;
 }
 static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, size_t first, size_t total_n,
@@ -665,7 +684,7 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     if (chain_wait && ctx->chain_hogged && !scalars) {
         // the main stream (whose next kernel fills the machine) waits until the chains' block is placed: ~10 us when the
         // device is idle, at most 0.2 ms (400 000 cycles) when it is not
-        k_wait_started<<<1, 32, 0, s>>>(ctx->d_flags + 3, 400000);
+        k_wait_started<<<1, 32, 0, s>>>(ctx->d_flags + 3, 400000, ctx->d_dbg);
         ctx->launches++;
     }
     // Small batches are latency chains (one thread per set): [r_i]pk_i does not depend on H(m_i), so it leads the
@@ -722,6 +741,35 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
         for (int k = 0; k < H2D_SLICES; k++) CK(cudaStreamWaitEvent(s, ctx->ev_slice[k], 0));
         END(ST_HASH, s);
         CK(cudaStreamWaitEvent(g, ctx->ev_copy[H2D_SLICES - 1], 0));    // the signature-side MSM reads every set
+    }
+    // H(m_i) on the main stream (already launched piece by piece when the host copy is sliced)
+    auto launch_hash = [&]() -> int {
+        if (sliced) return 0;
+        BEGIN(ST_HASH, s);
+        if (small_hash) {
+            static const int map2 = getenv("BLSGPU_MAP_LANES2") ? atoi(getenv("BLSGPU_MAP_LANES2")) : 1;
+            if (map2) k_hash_map_lanes2<<<nblk(2 * n, 64), 64, 0, s>>>(d_sets, nullptr, nullptr, nullptr, 0, n, sm_hash_in);
+            else k_hash_map_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, sm_hash_in);
+            launch_prog_many(ctx, p_cof, s, n, sm_hash_in, 6, nullptr, 0, sm_hash_out, 6);
+            k_g2_hom_to_jac<<<nblk(n), 128, 0, s>>>(sm_hash_out, n, ctx->d_H);
+            ctx->launches += 2;
+        } else if (pair_hash) k_hash_sets_lanes2<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+        else if (n <= 8192) k_hash_sets_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+        else k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
+        END(ST_HASH, s);
+        return 0;
+    };
+    // BLSGPU_MSM_AFTER_HASH_MIN (off by default): the signature-side MSM waits for the hash kernel and runs beside
+    // [r_i]pk_i and the line evaluations instead.  Measured at 131 072 sets: hash 26.1 -> 24.0 ms (its time alone), [r_i]pk_i
+    // +0.9, lines +1.3, step 57.3 -> 57.1 ms whatever the length of the scalar chain — but the starved MSM then ends only
+    // 1-2 ms before the join, so the gain is not worth the exposure.
+    static const size_t msm_after_hash_min = getenv("BLSGPU_MSM_AFTER_HASH_MIN") ? (size_t)atoll(getenv("BLSGPU_MSM_AFTER_HASH_MIN")) : ~(size_t)0;
+    const bool msm_after_hash = ctx->use_side && n >= msm_after_hash_min;
+    if (msm_after_hash) {
+        rc = launch_hash();
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev[EV_HASHED], s));
+        CK(cudaStreamWaitEvent(g, ctx->ev[EV_HASHED], 0));
     }
     BEGIN(ST_G2MUL, g);
     // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
@@ -792,20 +840,10 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
         if (rc) return rc;
     }
     if (ctx->use_side) CK(cudaEventRecord(ctx->ev[EV_JOIN], g));
-    if (!sliced) BEGIN(ST_HASH, s);
-    if (sliced) {
-        // hashed piece by piece above
-    } else if (small_hash) {
-        static const int map2 = getenv("BLSGPU_MAP_LANES2") ? atoi(getenv("BLSGPU_MAP_LANES2")) : 1;
-        if (map2) k_hash_map_lanes2<<<nblk(2 * n, 64), 64, 0, s>>>(d_sets, nullptr, nullptr, nullptr, 0, n, sm_hash_in);
-        else k_hash_map_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, sm_hash_in);
-        launch_prog_many(ctx, p_cof, s, n, sm_hash_in, 6, nullptr, 0, sm_hash_out, 6);
-        k_g2_hom_to_jac<<<nblk(n), 128, 0, s>>>(sm_hash_out, n, ctx->d_H);
-        ctx->launches += 2;
-    } else if (pair_hash) k_hash_sets_lanes2<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
-    else if (n <= 8192) k_hash_sets_pair<<<nblk(2 * n), 128, 0, s>>>(d_sets, n, ctx->d_H);
-    else k_hash_sets<<<nblk(n), 128, 0, s>>>(d_sets, n, ctx->d_H);
-    if (!sliced) END(ST_HASH, s);
+    if (!msm_after_hash) {
+        rc = launch_hash();
+        if (rc) return rc;
+    }
     if (g1_aside) {
         CK(cudaStreamWaitEvent(s, ctx->ev[EV_G1], 0));
     } else {

@@ -164,6 +164,29 @@ def test_epoch_batch_full_size_properties(br, srb):
         w0 = victim - 700
         window = bad[w0 * 320:(w0 + 1500) * 320]
         assert big.verify_raw(window, srb, 16, want_gt=True) == br.batch_verify(window, srb, 16)
+        # the same batch resident in device memory (blsgpu_batch_verify_dev: one launch per stage instead of the sliced
+        # copy/hash pipeline of the host call)
+        import torch
+        L = bg.lib()
+        d = torch.frombuffer(bytearray(bad), dtype=torch.uint8).cuda()
+        gt2 = (C.c_uint8 * 576)()
+        for chunks in (1024, 16):
+            rc = L.blsgpu_batch_verify_dev(big.handle, C.c_void_p(d.data_ptr()), n, srb, chunks, None, gt2)
+            assert rc == 0, big.last_error()
+            if chunks == 1024:
+                assert bytes(gt2) == gt
+        # a batch just past one wave of blocks (75 776 sets) of the thread-per-set kernels
+        n2 = 76000
+        rc = L.blsgpu_batch_verify_dev(big.handle, C.c_void_p(d.data_ptr()), n2, srb, 16, None, gt2)
+        assert rc == 1, big.last_error()
+        rc = L.blsgpu_batch_verify_dev(big.handle, C.c_void_p(d.data_ptr() + 320 * (victim - 75990)), n2, srb, 16, None, gt2)
+        assert rc == 0, big.last_error()
+        parts = b""
+        sub = bad[(victim - 75990) * 320:(victim - 75990 + n2) * 320]
+        for r in range(3):
+            first, cnt = bg.shard_range(n2, 3, r)
+            parts += be.partial(sub[first * 320:(first + cnt) * 320], first, n2, srb, 16)[0]
+        assert be.finalize(parts) == (False, bytes(gt2))
     finally:
         big.close()
 
