@@ -209,15 +209,10 @@ extern "C" blsgpu_ctx *blsgpu_create(int device, size_t max_sets) {
     ALLOC(ctx->d_srb, 32);
 #undef ALLOC
     if ((e = cudaMallocHost((void **)&ctx->h_pinned, 4096)) != cudaSuccess) return bad("cudaMallocHost", e);
-    if ((e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB1, FROB1, sizeof(FROB1), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
-        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB2, FROB2, sizeof(FROB2), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
-        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_FROB3, FROB3, sizeof(FROB3), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess)
-        return bad("cudaMemcpyFromSymbol(FROB)", e);
-    if ((e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_PSI_CX, PSI_CX, sizeof(PSI_CX), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
-        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_PSI_CY, PSI_CY, sizeof(PSI_CY), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
-        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_PSI2_CX, PSI2_CX, sizeof(PSI2_CX), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
-        (e = cudaMemcpyFromSymbol(ctx->d_consts + fpprog::CONST_ONE, FP_ONE, sizeof(FP_ONE), 0, cudaMemcpyDeviceToDevice)) != cudaSuccess)
-        return bad("cudaMemcpyFromSymbol(PSI)", e);
+    // the programs' constant table, filled by a kernel from the __constant__ tables (a device-to-device
+    // cudaMemcpyFromSymbol does the same, but compute-sanitizer's initcheck does not see constant memory as initialised)
+    k_fill_consts<<<1, 64>>>(ctx->d_consts);
+    if ((e = cudaGetLastError()) != cudaSuccess) return bad("k_fill_consts", e);
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bad("cudaDeviceSynchronize", e);
     ctx->serial_tail = getenv("BLSGPU_SERIAL_TAIL") && atoi(getenv("BLSGPU_SERIAL_TAIL")) != 0;
     if (getenv("BLSGPU_ACC_TEAM")) ctx->acc_team = atoi(getenv("BLSGPU_ACC_TEAM")) != 0;
@@ -307,6 +302,9 @@ static words8 words_of(const uint8_t b[32]) {
 
 #define BEGIN(stage, st) CK(cudaEventRecord(ctx->ev[2 * (stage)], st))
 #define END(stage, st) CK(cudaEventRecord(ctx->ev[2 * (stage) + 1], st))
+static_assert(fpprog::CONST_COUNT == fpprog_const_count && fpprog::CONST_FROB1 == 0 && fpprog::CONST_FROB2 == 10 &&
+                  fpprog::CONST_FROB3 == 20 && fpprog::CONST_PSI_CX == 30 && fpprog::CONST_PSI_CY == 32 &&
+                  fpprog::CONST_PSI2_CX == 34 && fpprog::CONST_ONE == 35, "k_fill_consts layout");
 #define EV_FORK (2 * ST_COUNT)
 #define EV_JOIN (2 * ST_COUNT + 1)
 #define EV_G1 (2 * ST_COUNT + 2)

@@ -23,6 +23,8 @@
 
 namespace bls {
 
+constexpr int fpprog_const_count = 36;                    // == fpprog::CONST_COUNT (static_assert in blsgpu.cu)
+
 // heavy kernels: at most 128 registers -> 4 blocks of 128 threads (16 warps, 4 per scheduler) per SM
 #ifndef BLS_LB_BLOCKS
 #define BLS_LB_BLOCKS 4
@@ -732,6 +734,22 @@ __global__ void k_partial_seal(const int *flags, uint32_t *partial, int *flag_ou
 // operation l.  A slot written
 // in round r is never read in round r (fpprog.hpp frees slots only after their last reading round), so one warp
 // barrier per round orders everything.
+// constant table of the dataflow programs (fpprog::CONST_*), copied from the __constant__ tables of consts.cuh
+__global__ void k_fill_consts(fp *dst) {
+    const int t = threadIdx.x;
+    if (t >= fpprog_const_count) return;
+    const fp *src;
+    int k;
+    if (t < 10) { src = (const fp *)FROB1; k = t; }
+    else if (t < 20) { src = (const fp *)FROB2; k = t - 10; }
+    else if (t < 30) { src = (const fp *)FROB3; k = t - 20; }
+    else if (t < 32) { src = (const fp *)&PSI_CX; k = t - 30; }
+    else if (t < 34) { src = (const fp *)&PSI_CY; k = t - 32; }
+    else if (t < 35) { src = &PSI2_CX; k = 0; }
+    else { src = &FP_ONE; k = 0; }
+    dst[t] = src[k];
+}
+
 // One warp per block; block b runs the program on instance b: in0 + b * s_in0, in1 + b * s_in1, out0 + b * s_out
 // (strides in field elements; the per-batch tails launch one block with zero strides, the small-batch route one block
 // per signature set).
