@@ -466,12 +466,24 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
                 const double cost = acc + gtp + 0.22 + 7.4e-3 * ns;
                 if (best == 0.0 || cost < best) { best = cost; G = g; nseg = ns; }
             }
-    } else if (team) {                             // ~32k teams: 6 lanes each, squarings are cheap to share widely
-        G = 1;
-        while (G < 16 && np / (size_t)(2 * G) >= 4096) G *= 2;
-        size_t ngroups = (np + G - 1) / G;
-        size_t want = ((size_t)1 << 15) / ngroups;
-        nseg = want < 1 ? 1 : (want > 32 ? 32 : (int)want);
+    } else if (team) {
+        // Throughput regime.  The Fp12 squarings of a step are shared by the G pairs of a group (work per pair ~ 884 + 756 / G
+        // multiplications), and short segments keep the tail of the grid short: swept on B200 (profiles/r2): 16 384 sets
+        // G = 8 / 16 segments (2.14 -> 1.82 ms), 32 768 and 65 536: G = 16 / 16 (3.79 -> 3.51, 7.08 -> 6.59), 131 072:
+        // G = 24 / 8 (14.3 -> 13.1 ms); past ~65 000 teams the product trees and the segment Horner eat the gain.
+        static const int old_rule = getenv("BLSGPU_ACC_OLD_RULE") ? atoi(getenv("BLSGPU_ACC_OLD_RULE")) : 0;
+        if (old_rule) {
+            G = 1;
+            while (G < 16 && np / (size_t)(2 * G) >= 4096) G *= 2;
+            size_t ngroups = (np + G - 1) / G;
+            size_t want = ((size_t)1 << 15) / ngroups;
+            nseg = want < 1 ? 1 : (want > 32 ? 32 : (int)want);
+        } else {
+            G = np < 24576 ? 8 : (np < 98304 ? 16 : 24);
+            const size_t ngroups = (np + G - 1) / G;
+            nseg = 16;
+            while (nseg > 4 && ngroups * (size_t)nseg > 65536) nseg -= 4;
+        }
     } else {
         G = 1;
         while (G < 8 && np / (size_t)(2 * G) >= 8192) G *= 2;
