@@ -460,9 +460,13 @@ static void miller_shape(size_t np, bool team, int &G, int &nseg) {
                 if (ngroups * ns > 32768) continue;             // d_F holds at least 40 000 (group, segment) products
                 const double waves = (double)((ngroups * ns + 11999) / 12000);
                 const double acc = waves * (double)((63 + ns - 1) / ns) * (1 + g) * (g <= 16 ? 7.5e-3 : 9.5e-3);
+                int levels = 0;                                 // product trees of eight (k_fp_program_rows), ~0.03 ms a level
+                for (size_t m = ngroups; m > 1; m = (m + 7) / 8) levels++;
+                static const int old_gtp = getenv("BLSGPU_ACC_OLD_RULE") ? atoi(getenv("BLSGPU_ACC_OLD_RULE")) : 0;
                 int depth = 0;
                 while (((size_t)1 << depth) < ngroups) depth++;
-                const double gtp = ngroups <= 8 ? 0.04 : (ngroups <= 64 ? 0.08 : (ngroups <= 128 ? 0.084 * depth : 1.16));
+                const double gtp = old_gtp ? (ngroups <= 8 ? 0.04 : (ngroups <= 64 ? 0.08 : (ngroups <= 128 ? 0.084 * depth : 1.16)))
+                                           : 0.01 + 0.03 * levels;
                 const double cost = acc + gtp + 0.22 + 7.4e-3 * ns;
                 if (best == 0.0 || cost < best) { best = cost; G = g; nseg = ns; }
             }
