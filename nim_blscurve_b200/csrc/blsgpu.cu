@@ -436,11 +436,15 @@ static size_t small_lines_max() {
     return v > 16385 ? 16385 : v;
 }
 #define SMALL_ROUTE_MAX SMALL_ROUTE_CAP   /* buffer strides */
-// Mid-size route: two lanes per set for H(m_i) and the line evaluations (fp2h.cuh) while a thread per set leaves the
-// machine under-filled: 148 SMs x 512 resident threads = 75 776 lanes, i.e. up to ~38k sets in one wave of lane pairs.
+// Two lanes per set for H(m_i) and the line evaluations (fp2h.cuh).  Introduced for mid-size batches, where a thread per
+// set leaves the machine under-filled; measured again at the end of round 2 (profiles/r2/r2_probe_routes_large.log) it
+// also wins for large ones: a block of lane pairs runs half as long as a block of threads, so the grid ends on a finer
+// wave boundary (81 920 sets: 43.1 -> 36.3 ms, 114 688: 52.6 -> 49.0), and the halved stacks stay in L2.  Lines: lane
+// pairs up to 180 000 pairs; hash: up to 125 000 sets (at 131 072 the thread-per-set hash with its 1.73 waves is the
+// quicker one: 55.0 ms against 55.4 with lane pairs for both and 55.8 with threads for both); beyond, threads.
 static size_t pair_hash_min() { static const size_t v = getenv("BLSGPU_PAIR_HASH_MIN") ? (size_t)atoll(getenv("BLSGPU_PAIR_HASH_MIN")) : 2049; return v; }
-static size_t pair_hash_max() { static const size_t v = getenv("BLSGPU_PAIR_HASH_MAX") ? (size_t)atoll(getenv("BLSGPU_PAIR_HASH_MAX")) : 40000; return v; }
-static size_t pair_lines_max() { static const size_t v = getenv("BLSGPU_PAIR_LINES_MAX") ? (size_t)atoll(getenv("BLSGPU_PAIR_LINES_MAX")) : 40000; return v; }
+static size_t pair_hash_max() { static const size_t v = getenv("BLSGPU_PAIR_HASH_MAX") ? (size_t)atoll(getenv("BLSGPU_PAIR_HASH_MAX")) : 125000; return v; }
+static size_t pair_lines_max() { static const size_t v = getenv("BLSGPU_PAIR_LINES_MAX") ? (size_t)atoll(getenv("BLSGPU_PAIR_LINES_MAX")) : 180000; return v; }
 #define SMALL_FP_PER_SET (6 + 6 + 6 + 6 + 64)
 
 // Work decomposition of the accumulation: G pairs per group (they share the Fp12 squarings) and nseg loop segments,
@@ -701,19 +705,6 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
         k_wait_started<<<1, 32, 0, s>>>(ctx->d_flags + 3, 400000, ctx->d_dbg);
         ctx->launches++;
     }
-    // Small batches are latency chains (one thread per set): [r_i]pk_i does not depend on H(m_i), so it leads the
-    // second stream instead of queueing behind the hash kernel.  Large batches fill the machine either way.
-    // measured (profiles/r2): beside the hash up to 8 192 sets (4 096 sets: 7.4 -> 6.7 ms); past that the two contend
-    static const size_t g1_aside_max = getenv("BLSGPU_G1_ASIDE_MAX") ? (size_t)atoll(getenv("BLSGPU_G1_ASIDE_MAX")) : 8192;
-    const bool g1_aside = ctx->use_side && n <= g1_aside_max;
-    if (g1_aside) {
-        cudaStream_t g1s = ctx->side2;
-        CK(cudaStreamWaitEvent(g1s, ctx->ev[EV_SC], 0));
-        BEGIN(ST_G1MUL, g1s);
-        k_g1_mul<<<nblk(n), 128, 0, g1s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
-        END(ST_G1MUL, g1s);
-        CK(cudaEventRecord(ctx->ev[EV_G1], g1s));
-    }
     // Small-batch route: the serial stretches of a set (cofactor clearing, [r_i] sig_i) run as per-set dataflow
     // programs, one warp per set (fpprog.hpp build_g2_clear_cofactor / build_g2_mul64)
     static const int small_env = getenv("BLSGPU_SMALL_ROUTE") ? atoi(getenv("BLSGPU_SMALL_ROUTE")) : 15;   // bit 0 hash, bit 1 sig (bit 2: lines, bit 3: GT product, run_miller)
@@ -755,6 +746,24 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
         for (int k = 0; k < H2D_SLICES; k++) CK(cudaStreamWaitEvent(s, ctx->ev_slice[k], 0));
         END(ST_HASH, s);
         CK(cudaStreamWaitEvent(g, ctx->ev_copy[H2D_SLICES - 1], 0));    // the signature-side MSM reads every set
+    }
+    // Small batches are latency chains (one thread per set): [r_i]pk_i does not depend on H(m_i), so it leads the
+    // second stream instead of queueing behind the hash kernel.  Large batches: behind a scalar chain of several
+    // milliseconds it starts while the hash kernel is in its last wave and fills the slots that wave leaves empty.
+    // measured (profiles/r2): beside the hash up to 8 192 sets (4 096 sets: 7.4 -> 6.7 ms) and from 36 000 on (49 152:
+    // 25.5 -> 24.1 ms, 65 536: 31.7 -> 30.3, 98 304: 45.8 -> 43.8, 131 072: 56.2 -> 55.9); between, the chain is short,
+    // the two run side by side from the start and contend (9 000 sets: 8.4 -> 9.1 ms)
+    static const size_t g1_aside_max = getenv("BLSGPU_G1_ASIDE_MAX") ? (size_t)atoll(getenv("BLSGPU_G1_ASIDE_MAX")) : 8192;
+    static const size_t g1_aside_large = getenv("BLSGPU_G1_ASIDE_LARGE_MIN") ? (size_t)atoll(getenv("BLSGPU_G1_ASIDE_LARGE_MIN")) : 36000;
+    const bool g1_aside = ctx->use_side && (n <= g1_aside_max || n >= g1_aside_large);
+    if (g1_aside) {
+        cudaStream_t g1s = ctx->side2;
+        CK(cudaStreamWaitEvent(g1s, ctx->ev[EV_SC], 0));
+        if (sliced) CK(cudaStreamWaitEvent(g1s, ctx->ev_copy[H2D_SLICES - 1], 0));   // the keys of every slice are in place
+        BEGIN(ST_G1MUL, g1s);
+        k_g1_mul<<<nblk(n), 128, 0, g1s>>>(d_sets, ctx->d_r, n, ctx->d_Pj, ctx->d_flags);
+        END(ST_G1MUL, g1s);
+        CK(cudaEventRecord(ctx->ev[EV_G1], g1s));
     }
     // H(m_i) on the main stream (already launched piece by piece when the host copy is sliced)
     auto launch_hash = [&]() -> int {

@@ -208,3 +208,44 @@ def test_route_boundaries_vs_blst(br, srb, n):
         assert c.verify_raw(bytes(bad), srb, 32, want_gt=True) == br.batch_verify(bytes(bad), srb, 32)
     finally:
         c.close()
+
+
+def test_thread_per_set_route_vs_blst(br, srb):
+    """The thread-per-set kernels (k_hash_sets, k_miller_lines) serve only very large batches by default (hash beyond
+    125 000 sets, lines beyond 180 000 pairs); a child process with the lane-pair routes switched off runs them on a
+    9 000-set batch, valid and with one corrupted set, and the verdicts and GT bytes are compared with BLST's here."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import ctypes as C, hashlib, sys
+sys.path.insert(0, %r)
+import nim_blscurve_b200 as bg
+srb = bytes.fromhex(%r)
+n = 9000
+c = bg.BatchedBLSVerifierCache(max_sets=n, device=0)
+out = (C.c_uint8 * (320 * n))()
+assert bg.lib().blsgpu_make_sets(c.handle, 4242, 0, n, out, 0) == 0
+sets = bytes(out)
+print("valid", c.verify_raw(sets, srb, 16))
+bad = bytearray(sets); bad[4321 * 320 + 97] ^= 0x02
+ok, gt = c.verify_raw(bytes(bad), srb, 16, want_gt=True)
+print("bad", ok, gt.hex())
+''' % (root, srb.hex())
+    env = dict(os.environ, BLSGPU_PAIR_HASH_MAX="1", BLSGPU_PAIR_LINES_MAX="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "valid True"
+    tag, ok, gt_hex = lines[1].split()
+    import nim_blscurve_b200 as bg
+    c = bg.BatchedBLSVerifierCache(max_sets=9000, device=0)
+    try:
+        out = (C.c_uint8 * (320 * 9000))()
+        assert bg.lib().blsgpu_make_sets(c.handle, 4242, 0, 9000, out, 0) == 0
+    finally:
+        c.close()
+    bad = bytearray(bytes(out))
+    bad[4321 * 320 + 97] ^= 0x02
+    rok, rgt = br.batch_verify(bytes(bad), srb, 16)
+    assert (ok == "True", bytes.fromhex(gt_hex)) == (rok, rgt)
