@@ -797,7 +797,7 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     BEGIN(ST_G2MUL, g);
     // S = sum_i [r_i] sig_i : Pippenger over the signatures in place (stride 320) for batches that can fill the
     // buckets, n independent 64-bit multiplications + tree below that
-    static const size_t g2_msm_min = getenv("BLSGPU_G2_MSM_MIN") ? (size_t)atoll(getenv("BLSGPU_G2_MSM_MIN")) : 2048;
+    static const size_t g2_msm_min = getenv("BLSGPU_G2_MSM_MIN") ? (size_t)atoll(getenv("BLSGPU_G2_MSM_MIN")) : 2500;   // swept: 2 048 sets 6.54 -> 6.13 ms with the per-set programs, 2 600: 6.39 -> 6.33 with the MSM
     if (n >= g2_msm_min) {
         std::string err;
         rc = msm_run<fp2>(ctx->msm, (const uint8_t *)d_sets + offsetof(sigset, sig), sizeof(sigset), (const uint8_t *)ctx->d_r, 8,
@@ -827,13 +827,14 @@ static int run_partial_impl(blsgpu_ctx *ctx, const sigset *d_sets, size_t n, siz
     k_sig_pair<<<1, 32, 0, g>>>(ctx->d_S, n, ctx->d_Q, ctx->d_P);
     ctx->launches++;
     END(ST_G2SUM, g);
-    // From 8 192 sets on the n set pairs do not wait for the signature sum (scalar chain, then the signature-side MSM: 4 ms
+    // From 4 500 sets on the n set pairs do not wait for the signature sum (scalar chain, then the signature-side MSM: 4 ms
     // at 8 192 sets, tens of milliseconds behind the long chains of a large batch).  Pair number n = (S, -G1) gets its own
     // one-pair Miller loop right here on the side stream, with buffers of its own, beside the big loop of the main stream;
     // after the join the two values are multiplied (one Fp12 product program).  Same product of the same n + 1 Miller
     // values, hence same GT.  Measured: 8 192 sets 8.10 -> 7.24 ms, 16 384: 11.1 -> 10.5, 32 768: 18.05 -> 17.2,
-    // 131 072: 57.7 -> 57.0; below 8 192 the extra loop costs more than the wait it removes (4 096: 6.5 -> 6.9 ms).
-    static const size_t defer_min = getenv("BLSGPU_DEFER_SIG_MIN") ? (size_t)atoll(getenv("BLSGPU_DEFER_SIG_MIN")) : 8192;
+    // 131 072: 57.7 -> 57.0; re-swept at the end of the round: it pays from ~4 500 sets on (4 800: 7.0 -> 6.87 ms, 6 000: 7.2 -> 7.0;
+    // 4 096: 6.55 -> 6.60, 3 000: 6.44 -> 6.51).
+    static const size_t defer_min = getenv("BLSGPU_DEFER_SIG_MIN") ? (size_t)atoll(getenv("BLSGPU_DEFER_SIG_MIN")) : 4500;
     const bool defer_sig = ctx->use_side && !ctx->serial_tail && n >= defer_min && !scalars;
     if (defer_sig) {
         const size_t per = (size_t)ML_NLINES * 6;

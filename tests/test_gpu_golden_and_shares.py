@@ -191,7 +191,7 @@ def test_epoch_batch_full_size_properties(br, srb):
         big.close()
 
 
-@pytest.mark.parametrize("n", [127, 128, 129, 1024, 1025, 2047, 2048, 2049, 4096, 4097, 6000, 8192, 8193, 9000])
+@pytest.mark.parametrize("n", [127, 128, 129, 1024, 1025, 2047, 2048, 2049, 2499, 2500, 4096, 4097, 4499, 4500, 6000, 8192, 8193, 9000])
 def test_route_boundaries_vs_blst(br, srb, n):
     """The batch pipeline picks its kernels by batch size (warp-per-set programs up to 4 096 sets, two lanes per message
     up to 8 192, a thread per set beyond; the G2 sum switches to Pippenger at 2 048): one batch just past each boundary,
